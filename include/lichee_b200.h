@@ -1,0 +1,140 @@
+/*
+ * lichee_b200.h -- C ABI of the B200 lineage-tree search (libLICHeE_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of LICHeE's `-build` command: the enumeration of
+ * the spanning trees of the evolutionary constraint network, the per-sample VAF sum-rule check,
+ * and the error scoring + ranking of the valid trees.  Everything either side of it (SSNV
+ * loading, clustering, network construction, GUI, DOT export) stays in the Java host.
+ *
+ * Reference interfaces replaced (LICHeE/src/lineage):
+ *   PHYNetwork.getLineageTrees()        PHYNetwork.java:547-565  -> lichee_search_run
+ *   PHYNetwork.grow(PHYTree)            PHYNetwork.java:443-541  -> device frontier expansion
+ *   PHYTree.checkConstraint(PHYNode)    PHYTree.java:156-174     -> device sum-rule check
+ *   PHYTree.computeErrorScore()         PHYTree.java:214-233     -> device scoring
+ *   PHYNetwork.evaluateLineageTrees()   PHYNetwork.java:726-733  -> device top-s selection
+ *   LineageEngine.buildLineage step 5/6 LineageEngine.java:106-134 (caller)
+ *
+ * Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary.
+ * All functions return LICHEE_OK (0) or a negative error code; lichee_last_error() gives text.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * LICHEE_ERR_NO_DEVICE.
+ */
+#ifndef LICHEE_B200_H
+#define LICHEE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LICHEE_OK                 0
+#define LICHEE_ERR_INVALID       -1   /* bad argument (null pointer, size out of range)          */
+#define LICHEE_ERR_NO_DEVICE     -2   /* no CUDA device / CUDA runtime error                     */
+#define LICHEE_ERR_CYCLIC        -3   /* constraint network is not a DAG                         */
+#define LICHEE_ERR_TOO_LARGE     -4   /* more than LICHEE_MAX_NODES nodes / LICHEE_MAX_SAMPLES   */
+#define LICHEE_ERR_CUDA          -5   /* a CUDA call failed; see lichee_last_error()             */
+#define LICHEE_ERR_STATE         -6   /* call order violated (e.g. result before run)            */
+
+#define LICHEE_MAX_NODES    128       /* network nodes including the germline root (node 0)      */
+#define LICHEE_MAX_SAMPLES   64
+#define LICHEE_MAX_SAVE    1024       /* upper bound on -s                                       */
+
+/* status bits returned in lichee_search_stats.status */
+#define LICHEE_STATUS_TREE_CAP   1u   /* stopped at max_num_trees   (Parameters.MAX_NUM_TREES)      */
+#define LICHEE_STATUS_GROW_CAP   2u   /* stopped at max_num_grow_calls (Parameters.MAX_NUM_GROW_CALLS) */
+
+typedef struct lichee_search lichee_search;   /* opaque handle: one constraint network on one GPU */
+
+/* Search parameters.  Field <-> reference parameter:
+ *   vaf_error_margin    -e                     Parameters.VAF_ERROR_MARGIN      (default 0.1)
+ *   num_save            -s                     LineageEngine.Args.numSave       (default 1)
+ *   max_num_trees       Parameters.MAX_NUM_TREES        (default 100000)
+ *   max_num_grow_calls  Parameters.MAX_NUM_GROW_CALLS   (default 100000000)
+ * -minRobustNodeSupport acts before this boundary (it decides which clusters are robust, hence
+ * which nodes PHYNetwork.fixNetwork removes between two searches); the host re-submits the
+ * adjusted network, see INTEGRATION.md.
+ * part_rank/part_count shard one search over several GPUs: the frontier at the first tree levels
+ * is cut into part_count contiguous slices of the canonical enumeration order and this handle
+ * searches slice part_rank (0/1 = the whole search).
+ */
+typedef struct lichee_search_params {
+    double  vaf_error_margin;
+    int32_t num_save;
+    int32_t device;              /* CUDA device ordinal                                        */
+    int64_t max_num_trees;
+    int64_t max_num_grow_calls;
+    int32_t part_rank;
+    int32_t part_count;
+    int64_t level_capacity;      /* frontier items per tree level kept in HBM; 0 = default      */
+    int64_t reserved[4];
+} lichee_search_params;
+
+typedef struct lichee_search_stats {
+    int64_t num_trees;           /* valid spanning trees found ("Found N valid tree(s)")        */
+    int64_t num_grow_calls;      /* accepted partial trees + 1, the reference's numGrowCalls    */
+    int64_t num_checks;          /* checkConstraint evaluations (candidate trees checked)       */
+    int64_t num_scored;          /* complete trees scored                                       */
+    int64_t num_launches;        /* kernels launched by lichee_search_run                       */
+    int64_t frontier_bytes;      /* algorithmic HBM bytes moved through the frontier buffers    */
+    double  kernel_ms_check;     /* summed CUDA-event time of the sum-rule check kernel         */
+    double  kernel_ms_total;     /* CUDA-event time of the whole device search                  */
+    uint32_t status;
+    uint32_t num_saved;          /* trees held in the ranked list, <= num_save                  */
+} lichee_search_stats;
+
+void lichee_default_params(lichee_search_params *p);
+
+/* Ship one constraint network to the device.
+ *   n_nodes, n_samples : PHYNetwork.numNodes / numSamples; node 0 is the germline root.
+ *   adj_off[n_nodes+1], adj_idx[adj_off[n_nodes]] : PHYNetwork.edges as CSR, children of node i in
+ *       adjacency-list order (PHYNetwork.java:75).
+ *   vaf[n_nodes * n_samples] : PHYNode.getAAF(sample) per node, row-major; row 0 = VAF_MAX.
+ * The arrays are HOST memory and are copied; they may be freed after the call returns. */
+int lichee_search_create(lichee_search **out, int32_t n_nodes, int32_t n_samples,
+                         const int32_t *adj_off, const int32_t *adj_idx, const double *vaf,
+                         const lichee_search_params *params);
+
+/* getLineageTrees() + evaluateLineageTrees(): enumerate, check, score, rank.  Blocking. */
+int lichee_search_run(lichee_search *h);
+
+int lichee_search_get_stats(const lichee_search *h, lichee_search_stats *out);
+
+/* Ranked tree k (0 = lowest error score), k < stats.num_saved.
+ *   score      : PHYTree.getErrorScore()
+ *   parent[n]  : parent node of every node (-1 for the root)        -> PHYTree.treeEdges
+ *   order[n]   : nodes in the order they join the tree, root first  -> PHYTree.treeNodes; the
+ *                children of a node, taken in this order, are its treeEdges list
+ *   seq        : position of the tree in the enumeration order (ties in score rank by it)      */
+int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int32_t *parent,
+                           int32_t *order, int64_t *seq);
+
+/* Multi-GPU merge: raw ranked list of this handle (for an allgather) and its inverse.
+ * A record is lichee_record_bytes(h) bytes: {double score; int64 seq; int32 part; int32 pad;
+ * uint8 parent_of_position[stride]}.  Records stay in DEVICE memory when `device_ptr` is
+ * non-zero (so NCCL can move them), else they are copied to the host buffer. */
+int64_t lichee_record_bytes(const lichee_search *h);
+int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_ptr);
+int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_lists, int device_ptr);
+
+/* Canonical enumeration order of this network: sigma[i] = node assigned at tree level i+1
+ * (n_nodes-1 entries).  Used by tests and by hosts that want to reproduce `seq`. */
+int lichee_search_get_order(const lichee_search *h, int32_t *sigma);
+
+int lichee_search_destroy(lichee_search *h);
+
+/* One-shot convenience used by the JNI stub: create + run + copy the ranked list out.
+ * scores[num_save], parents[num_save*n_nodes], orders[num_save*n_nodes]. */
+int lichee_get_lineage_trees(int32_t n_nodes, int32_t n_samples, const int32_t *adj_off,
+                             const int32_t *adj_idx, const double *vaf,
+                             const lichee_search_params *params, lichee_search_stats *stats,
+                             double *scores, int32_t *parents, int32_t *orders);
+
+const char *lichee_last_error(void);
+const char *lichee_version(void);
+int lichee_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LICHEE_B200_H */

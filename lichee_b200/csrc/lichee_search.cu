@@ -1,0 +1,1050 @@
+// lichee_search.cu -- B200 (sm_100a) lineage-tree search behind the C ABI in include/lichee_b200.h.
+//
+// What it replaces in the reference (LICHeE/src/lineage):
+//   PHYNetwork.getLineageTrees / grow      PHYNetwork.java:443-565  spanning-tree enumeration
+//   PHYTree.checkConstraint                PHYTree.java:156-174     per-sample VAF sum rule
+//   PHYTree.computeErrorScore / compareTo  PHYTree.java:214-237     error score, ranking
+//   PHYNetwork.evaluateLineageTrees        PHYNetwork.java:726-733  sort, keep the top -s
+//
+// Design (DESIGN.md has the long version):
+//   * The constraint network is a DAG with the germline root as its only source, so a spanning
+//     tree is exactly one parent choice per non-root node.  Nodes are placed in a fixed order
+//     sigma (descending VAF mass); a frontier item is the byte string of parents chosen so far.
+//   * One WARP extends one partial tree: lanes own samples (1 or 2 per lane), the centroid
+//     matrix lives in shared memory, the children of a candidate parent are found by comparing
+//     the item's parent bytes against the candidate and voting with __ballot_sync, and the
+//     per-sample sums are compared against parent VAF + margin with a warp vote.
+//   * The frontier is kept in HBM level by level and walked depth-first in chunks, so memory is
+//     bounded by (levels x level_capacity) and trees come out in a deterministic canonical order.
+//     check -> exclusive scan -> emit keeps that order without atomics.
+//   * Complete trees are scored in double precision in the reference's accumulation order
+//     (parents by descending id, samples ascending, positive terms only) and filtered against
+//     the current s-th best score; survivors go through a block-level bitonic top-s selection.
+//   No tensor cores: nothing here is a dense contraction.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/lichee_b200.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 16;                 // 512 threads share one copy of the matrix
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMaxN = LICHEE_MAX_NODES;
+constexpr int kSelThreads = 1024;
+constexpr int kSelTile = 1024;
+constexpr unsigned kFull = 0xffffffffu;
+
+thread_local std::string g_err;
+
+void set_err(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            set_err("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return LICHEE_ERR_CUDA;                                                      \
+        }                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device-side description of one network
+// ------------------------------------------------------------------------------------------
+struct DevNet {
+    const double *vaf;       // [n][SP]   centroid matrix, rows by node id, zero padded to SP
+    const uint8_t *sigma;    // [L]       node placed at tree level t (0-based position)
+    const uint8_t *cand;     // [L][128]  candidate parents of sigma[t], ascending node id
+    const uint8_t *ncand;    // [L]
+    int n, S, SP, L, stride; // stride = bytes per frontier item (multiple of 16, <= 128)
+    double margin;
+};
+
+struct Cand {                // one scored complete tree that beat the current threshold
+    double score;
+    long long seq;           // position in the canonical enumeration order (of this part)
+    int part;                // multi-GPU slice the tree came from
+    unsigned origin;         // index of the leaf-parent item (new) or slot | 0x80000000 (kept)
+    unsigned pstar;          // parent chosen for the last node (new entries)
+    unsigned pad;
+};
+
+struct TopMeta {             // device-resident state of the ranked list
+    unsigned count;          // trees currently held
+    unsigned pad;
+    double tau;              // score of the worst held tree once the list is full, else +inf
+    unsigned long long n_cand;  // candidates appended by the current leaf launch
+};
+
+struct ScanOut {             // written by the scan, read back by the host once per chunk
+    unsigned long long fit;  // (items that fit) << 32 | children they produce
+    unsigned long long total;
+};
+
+__device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b) {
+    if (a.score != b.score) return a.score < b.score;
+    if (a.part != b.part) return a.part < b.part;
+    return a.seq < b.seq;
+}
+
+// Shared-memory staging of the centroid matrix and the per-level tables.
+template <int SPL>
+__device__ __forceinline__ void stage_network(const DevNet &net, int level, double *vaf_s,
+                                              uint8_t *sigma_s, uint8_t *cand_s) {
+    const int words = net.n * net.SP;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) vaf_s[i] = net.vaf[i];
+    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) {
+        sigma_s[i] = i < net.L ? net.sigma[i] : 0;
+        cand_s[i] = net.cand[(size_t)level * kMaxN + i];
+    }
+    __syncthreads();
+}
+
+// Sum of the centroid rows of the children of candidate parent p inside item word-vector w
+// (lane l holds parent bytes 4l..4l+3), in ascending tree-level order: the canonical
+// accumulation order.  Returns the sums for samples lane and lane+32.
+template <int SPL>
+__device__ __forceinline__ void child_sums(unsigned w, unsigned p, const double *vaf_s,
+                                           const uint8_t *sigma_s, int SP, int lane, double &s0,
+                                           double &s1) {
+    const unsigned m = __vcmpeq4(w, p * 0x01010101u);
+    unsigned any = __ballot_sync(kFull, m != 0);
+    s0 = 0.0;
+    s1 = 0.0;
+    while (any) {
+        const int l = __ffs(any) - 1;
+        any &= any - 1;
+        const unsigned mm = __shfl_sync(kFull, m, l);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (mm & (0xffu << (8 * r))) {
+                const int c = sigma_s[l * 4 + r];
+                s0 = __dadd_rn(s0, vaf_s[c * SP + lane]);
+                if (SPL == 2) s1 = __dadd_rn(s1, vaf_s[c * SP + 32 + lane]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 1: sum-rule check.  One warp per frontier item; for every candidate parent of the node
+// placed at this level, test  sum(children VAF) + VAF(node) <= VAF(parent) + margin  per sample.
+// Output: 128-bit pass mask + pass count per item.
+// ------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(kThreads)
+check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long n_items,
+             uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vaf_s = reinterpret_cast<double *>(smem_raw);
+    uint8_t *sigma_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    uint8_t *cand_s = sigma_s + kMaxN;
+    stage_network<SPL>(net, level, vaf_s, sigma_s, cand_s);
+
+    const int lane = threadIdx.x & 31;
+    const int SP = net.SP;
+    const int k = net.ncand[level];
+    const int v = sigma_s[level];
+    const double xv0 = vaf_s[v * SP + lane];
+    const double xv1 = SPL == 2 ? vaf_s[v * SP + 32 + lane] : 0.0;
+    const bool valid0 = lane < net.S;
+    const bool valid1 = SPL == 2 && lane + 32 < net.S;
+    const int wstride = net.stride >> 2;
+    const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+
+    for (long long it = warp0; it < n_items; it += nwarps) {
+        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+        unsigned bits = 0, cnt = 0;
+        for (int i = 0; i < k; i++) {
+            const unsigned p = cand_s[i];
+            double s0, s1;
+            child_sums<SPL>(w, p, vaf_s, sigma_s, SP, lane, s0, s1);
+            s0 = __dadd_rn(s0, xv0);
+            bool bad = valid0 && s0 > __dadd_rn(vaf_s[p * SP + lane], net.margin);
+            if (SPL == 2) {
+                s1 = __dadd_rn(s1, xv1);
+                bad |= valid1 && s1 > __dadd_rn(vaf_s[p * SP + 32 + lane], net.margin);
+            }
+            if (!__any_sync(kFull, bad)) {
+                cnt++;
+                if (lane == (i >> 5)) bits |= 1u << (i & 31);
+            }
+        }
+        const unsigned b0 = __shfl_sync(kFull, bits, 0), b1 = __shfl_sync(kFull, bits, 1);
+        const unsigned b2 = __shfl_sync(kFull, bits, 2), b3 = __shfl_sync(kFull, bits, 3);
+        if (lane == 0) {
+            mask_out[it] = make_uint4(b0, b1, b2, b3);
+            count_out[it] = cnt;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels 2a-2c: exclusive scan of the pass counts (keeps the canonical order without atomics)
+// and the largest prefix of items whose children fit in the next level's buffer.
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 8;
+constexpr int kScanTile = kScanThreads * kScanPer;
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tiles(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned long long *tile_sum,
+           long long n) {
+    __shared__ unsigned warp_tot[kScanThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanPer;
+    unsigned v[kScanPer], run = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPer; i++) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        run += v[i];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    unsigned woff = 0;
+    for (int i = 0; i < wid; i++) woff += warp_tot[i];
+    unsigned ex = woff + inc - run;
+#pragma unroll
+    for (int i = 0; i < kScanPer; i++) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == kScanThreads - 1) tile_sum[blockIdx.x] = woff + inc;
+}
+
+__global__ void scan_tile_sums(unsigned long long *tile_sum, int n_tiles, ScanOut *out) {
+    // single thread block, serial over tiles: n_tiles <= a few thousand
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < n_tiles; i++) {
+            unsigned long long t = tile_sum[i];
+            tile_sum[i] = run;
+            run += t;
+        }
+        out->total = run;
+        out->fit = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
+            const unsigned long long *__restrict__ tile_sum, long long n, unsigned long long limit,
+            ScanOut *out) {
+    const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanPer;
+    const unsigned long long add = tile_sum[blockIdx.x];
+    unsigned long long best = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPer; i++) {
+        const long long idx = base + i;
+        if (idx < n) {
+            const unsigned long long ex = add + off[idx];
+            off[idx] = (unsigned)ex;
+            const unsigned long long inc = ex + cnt[idx];
+            if (inc <= limit) best = ((unsigned long long)(idx + 1) << 32) | inc;
+        }
+    }
+    if (best) atomicMax(&out->fit, best);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 3: emit.  One warp per parent item writes its surviving children, 128 coalesced bytes
+// per child, at the offsets the scan assigned (so children appear in canonical order).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+emit_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long n_items,
+            const uint4 *__restrict__ mask, const unsigned *__restrict__ off,
+            unsigned *__restrict__ out) {
+    __shared__ uint8_t cand_s[kMaxN];
+    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) cand_s[i] = net.cand[(size_t)level * kMaxN + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wstride = net.stride >> 2;
+    const int wl = level >> 2, sh = 8 * (level & 3);
+    const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long it = warp0; it < n_items; it += nwarps) {
+        const uint4 m4 = mask[it];
+        if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
+        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+        long long dst = (long long)off[it];
+        const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            unsigned b = mw[q];
+            while (b) {
+                const int i = q * 32 + __ffs(b) - 1;
+                b &= b - 1;
+                unsigned cw = w;
+                if (lane == wl) cw = (w & ~(0xffu << sh)) | ((unsigned)cand_s[i] << sh);
+                if (lane < wstride) out[dst * wstride + lane] = cw;
+                dst++;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 4: score complete trees.  One warp per leaf-parent item; every passing choice for the
+// last node is a complete valid tree.  Error score = sqrt( sum over parents (descending id) and
+// samples (ascending) of max(0, sum(children) - VAF(parent))^2 ), accumulated in exactly that
+// order like PHYTree.computeErrorScore.  Trees that beat the current threshold are appended to
+// the candidate list.
+// ------------------------------------------------------------------------------------------
+template <int SPL>
+__global__ void __launch_bounds__(kThreads)
+leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, long long item_base,
+            const uint4 *__restrict__ mask, const unsigned *__restrict__ off, long long seq_base,
+            long long max_trees, int part, TopMeta *meta, int num_save, Cand *__restrict__ cands,
+            long long cand_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vaf_s = reinterpret_cast<double *>(smem_raw);
+    uint8_t *sigma_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    uint8_t *cand_s = sigma_s + kMaxN;
+    const int level = net.L - 1;
+    stage_network<SPL>(net, level, vaf_s, sigma_s, cand_s);
+
+    const int lane = threadIdx.x & 31;
+    const int SP = net.SP;
+    const bool valid0 = lane < net.S;
+    const bool valid1 = SPL == 2 && lane + 32 < net.S;
+    const int wstride = net.stride >> 2;
+    const int wl = level >> 2, sh = 8 * (level & 3);
+    const double tau = meta->tau;
+    const bool full = meta->count >= (unsigned)num_save;
+    const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+
+    for (long long it = warp0; it < n_items; it += nwarps) {
+        const uint4 m4 = mask[it];
+        if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
+        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+        long long seq = seq_base + (long long)off[it];
+        const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
+        for (int q = 0; q < 4; q++) {
+            unsigned b = mw[q];
+            while (b) {
+                const int i = q * 32 + __ffs(b) - 1;
+                b &= b - 1;
+                const long long my_seq = seq++;
+                if (my_seq >= max_trees) continue;
+                const unsigned pstar = cand_s[i];
+                unsigned cw = w;
+                if (lane == wl) cw = (w & ~(0xffu << sh)) | (pstar << sh);
+                double err = 0.0;
+                for (int p = net.n - 1; p >= 0; p--) {
+                    const unsigned m = __vcmpeq4(cw, (unsigned)p * 0x01010101u);
+                    if (__ballot_sync(kFull, m != 0) == 0) continue;
+                    double s0, s1;
+                    child_sums<SPL>(cw, (unsigned)p, vaf_s, sigma_s, SP, lane, s0, s1);
+                    const double a0 = vaf_s[p * SP + lane];
+                    const bool pos0 = valid0 && s0 > a0;
+                    const double d0 = __dsub_rn(s0, a0);
+                    const double t0 = __dmul_rn(d0, d0);
+                    unsigned pb = __ballot_sync(kFull, pos0);
+                    while (pb) {
+                        const int l = __ffs(pb) - 1;
+                        pb &= pb - 1;
+                        err = __dadd_rn(err, __shfl_sync(kFull, t0, l));
+                    }
+                    if (SPL == 2) {
+                        const double a1 = vaf_s[p * SP + 32 + lane];
+                        const bool pos1 = valid1 && s1 > a1;
+                        const double d1 = __dsub_rn(s1, a1);
+                        const double t1 = __dmul_rn(d1, d1);
+                        pb = __ballot_sync(kFull, pos1);
+                        while (pb) {
+                            const int l = __ffs(pb) - 1;
+                            pb &= pb - 1;
+                            err = __dadd_rn(err, __shfl_sync(kFull, t1, l));
+                        }
+                    }
+                }
+                const double score = __dsqrt_rn(err);
+                if (!full || score < tau) {
+                    if (lane == 0) {
+                        const unsigned long long slot = atomicAdd(&meta->n_cand, 1ull);
+                        if ((long long)slot < cand_cap) {
+                            Cand c;
+                            c.score = score;
+                            c.seq = my_seq;
+                            c.part = part;
+                            c.origin = (unsigned)(item_base + it);
+                            c.pstar = pstar;
+                            c.pad = 0;
+                            cands[slot] = c;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 5: block-level top-s selection.  One block keeps the ranked list (<= 1024 trees) in
+// shared memory, streams the candidates through it in tiles with a bitonic sort of 2048 entries
+// (ties: lower part, then lower seq wins), then gathers the surviving trees' parent bytes into
+// the other half of the double-buffered tree store.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_2048(Cand *e) {
+    for (int k = 2; k <= 2 * kSelTile; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < 2 * kSelTile; t += kSelThreads) {
+                const int x = t ^ j;
+                if (x > t) {
+                    const bool up = (t & k) == 0;
+                    Cand a = e[t], b = e[x];
+                    if (cand_less(b, a) == up) {
+                        e[t] = b;
+                        e[x] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long long cand_cap,
+              Cand *top_cur, Cand *top_next, const unsigned *__restrict__ tree_cur,
+              unsigned *__restrict__ tree_next, const unsigned *__restrict__ leaf_items, int wstride,
+              int last_level, int external_records, const unsigned char *__restrict__ records,
+              long long record_bytes) {
+    extern __shared__ __align__(16) unsigned char sel_raw[];
+    Cand *e = reinterpret_cast<Cand *>(sel_raw);
+    const unsigned count = meta->count;
+    unsigned long long m = meta->n_cand;
+    if ((long long)m > cand_cap) m = (unsigned long long)cand_cap;
+    Cand sentinel;
+    sentinel.score = INFINITY;
+    sentinel.seq = 0x7fffffffffffffffll;
+    sentinel.part = 0x7fffffff;
+    sentinel.origin = 0xffffffffu;
+    sentinel.pstar = 0;
+    sentinel.pad = 1;   // pad == 1 marks a sentinel
+    for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) {
+        if ((unsigned)t < count) {
+            Cand c = top_cur[t];
+            c.origin = 0x80000000u | (unsigned)t;
+            e[t] = c;
+        } else {
+            e[t] = sentinel;
+        }
+    }
+    __syncthreads();
+    for (unsigned long long base = 0; base < m; base += kSelTile) {
+        for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
+            e[kSelTile + t] = base + t < m ? cands[base + t] : sentinel;
+        __syncthreads();
+        bitonic_sort_2048(e);
+    }
+    unsigned long long total = count + m;
+    const unsigned newc = (unsigned)(total < (unsigned long long)num_save ? total : (unsigned long long)num_save);
+    // gather parent bytes of the survivors
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int wl = last_level >> 2, sh = 8 * (last_level & 3);
+    for (unsigned t = wid; t < newc; t += kSelThreads / 32) {
+        const Cand c = e[t];
+        unsigned w = 0xffffffffu;
+        if (lane < wstride) {
+            if (c.origin & 0x80000000u) {
+                w = tree_cur[(size_t)(c.origin & 0x7fffffffu) * wstride + lane];
+            } else if (external_records) {
+                const unsigned *src = reinterpret_cast<const unsigned *>(records + (size_t)c.origin * record_bytes + 24);
+                w = src[lane];
+            } else {
+                w = leaf_items[(size_t)c.origin * wstride + lane];
+                if (lane == wl) w = (w & ~(0xffu << sh)) | (c.pstar << sh);
+            }
+            tree_next[(size_t)t * wstride + lane] = w;
+        }
+    }
+    for (int t = threadIdx.x; t < (int)newc; t += kSelThreads) top_next[t] = e[t];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        meta->count = newc;
+        meta->tau = newc >= (unsigned)num_save ? e[newc - 1].score : INFINITY;
+        meta->n_cand = 0;
+    }
+}
+
+__global__ void init_meta(TopMeta *meta) {
+    meta->count = 0;
+    meta->pad = 0;
+    meta->tau = INFINITY;
+    meta->n_cand = 0;
+}
+
+// unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
+__global__ void records_to_cands(const unsigned char *records, long long record_bytes, long long n,
+                                 Cand *cands, TopMeta *meta) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned char *r = records + i * record_bytes;
+        Cand c;
+        c.score = *reinterpret_cast<const double *>(r);
+        c.seq = *reinterpret_cast<const long long *>(r + 8);
+        c.part = *reinterpret_cast<const int *>(r + 16);
+        c.origin = (unsigned)i;
+        c.pstar = 0;
+        c.pad = 0;
+        const int valid = *reinterpret_cast<const int *>(r + 20);
+        if (!valid) { c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.pad = 1; }
+        cands[i] = c;
+    }
+    if (i == 0) { meta->count = 0; meta->tau = INFINITY; meta->n_cand = (unsigned long long)n; }
+}
+
+__global__ void export_records(const TopMeta *meta, const Cand *top, const unsigned *tree, int wstride,
+                               int num_save, unsigned char *records, long long record_bytes) {
+    const int t = blockIdx.x;
+    if (t >= num_save) return;
+    unsigned char *r = records + (size_t)t * record_bytes;
+    const bool valid = (unsigned)t < meta->count;
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<double *>(r) = valid ? top[t].score : INFINITY;
+        *reinterpret_cast<long long *>(r + 8) = valid ? top[t].seq : 0;
+        *reinterpret_cast<int *>(r + 16) = valid ? top[t].part : 0;
+        *reinterpret_cast<int *>(r + 20) = valid ? 1 : 0;
+    }
+    if ((int)threadIdx.x < wstride)
+        reinterpret_cast<unsigned *>(r + 24)[threadIdx.x] = valid ? tree[(size_t)t * wstride + threadIdx.x] : 0xffffffffu;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side of the handle
+// ------------------------------------------------------------------------------------------
+struct lichee_search {
+    int n = 0, S = 0, SP = 32, L = 0, stride = 16, device = 0;
+    lichee_search_params prm{};
+    std::vector<int> sigma;                  // node at position t
+    std::vector<std::vector<int>> cands;     // candidate parents per position
+    bool no_trees = false;                   // some node has no parent at all
+    bool ran = false;
+    lichee_search_stats stats{};
+    // device
+    cudaStream_t stream = nullptr;
+    double *d_vaf = nullptr;
+    uint8_t *d_sigma = nullptr, *d_cand = nullptr, *d_ncand = nullptr;
+    std::vector<unsigned *> d_level;         // lazily allocated frontier buffers
+    std::vector<long long> head, tail;
+    long long cap = 0;                       // items per level buffer
+    uint4 *d_mask = nullptr;
+    unsigned *d_cnt = nullptr, *d_off = nullptr;
+    unsigned long long *d_tile = nullptr;
+    ScanOut *d_scan = nullptr, *h_scan = nullptr;
+    TopMeta *d_meta = nullptr;
+    Cand *d_cands = nullptr, *d_top[2] = {nullptr, nullptr};
+    unsigned *d_tree[2] = {nullptr, nullptr};
+    int flip = 0;
+    long long chunk_max = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+    // results on host
+    std::vector<Cand> h_top;
+    std::vector<uint8_t> h_tree;
+    DevNet net{};
+    size_t smem = 0;
+};
+
+namespace {
+
+int grid_for(long long items) {
+    long long blocks = (items + kWarpsPerBlock * 4 - 1) / (kWarpsPerBlock * 4);
+    const long long maxb = 148 * 3;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int alloc_level(lichee_search *h, int lv) {
+    if (h->d_level[lv]) return LICHEE_OK;
+    CK(cudaMalloc(&h->d_level[lv], (size_t)h->cap * h->stride));
+    return LICHEE_OK;
+}
+
+template <int SPL>
+int launch_check(lichee_search *h, int lv, const unsigned *items, long long n_items) {
+    check_kernel<SPL><<<grid_for(n_items), kThreads, h->smem, h->stream>>>(h->net, lv, items, n_items,
+                                                                          h->d_mask, h->d_cnt);
+    CK(cudaGetLastError());
+    return LICHEE_OK;
+}
+
+int launch_scan(lichee_search *h, long long n_items, unsigned long long limit) {
+    const int tiles = (int)((n_items + kScanTile - 1) / kScanTile);
+    scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt, h->d_off, h->d_tile, n_items);
+    scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile, tiles, h->d_scan);
+    scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt, h->d_off, h->d_tile, n_items, limit, h->d_scan);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_scan, h->d_scan, sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
+    return LICHEE_OK;
+}
+
+int run_select(lichee_search *h, const unsigned *leaf_items, int external, const unsigned char *records,
+               long long record_bytes, long long cand_cap) {
+    const size_t sm = sizeof(Cand) * 2 * kSelTile;
+    select_kernel<<<1, kSelThreads, sm, h->stream>>>(h->d_meta, h->prm.num_save, h->d_cands, cand_cap,
+                                                     h->d_top[h->flip], h->d_top[h->flip ^ 1],
+                                                     h->d_tree[h->flip], h->d_tree[h->flip ^ 1], leaf_items,
+                                                     h->stride >> 2, h->L - 1, external, records, record_bytes);
+    CK(cudaGetLastError());
+    h->flip ^= 1;
+    h->stats.num_launches++;
+    return LICHEE_OK;
+}
+
+int fetch_top(lichee_search *h) {
+    TopMeta m;
+    CK(cudaMemcpyAsync(&m, h->d_meta, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->h_top.resize(m.count);
+    h->h_tree.assign((size_t)m.count * h->stride, 0xff);
+    if (m.count) {
+        CK(cudaMemcpyAsync(h->h_top.data(), h->d_top[h->flip], sizeof(Cand) * m.count, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_tree.data(), h->d_tree[h->flip], (size_t)m.count * h->stride, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->stats.num_saved = m.count;
+    return LICHEE_OK;
+}
+
+template <int SPL>
+int run_search(lichee_search *h) {
+    const int L = h->L;
+    lichee_search_stats &st = h->stats;
+    st = lichee_search_stats{};
+    st.num_grow_calls = 1;
+    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta);
+    h->flip = 0;
+    for (int lv = 0; lv < L; lv++) h->head[lv] = h->tail[lv] = 0;
+    if (h->no_trees || L == 0) return fetch_top(h);
+
+    CK(alloc_level(h, 0) == LICHEE_OK ? cudaSuccess : cudaErrorMemoryAllocation);
+    CK(cudaMemsetAsync(h->d_level[0], 0xff, h->stride, h->stream));
+    h->tail[0] = 1;
+    CK(cudaEventRecord(h->ev0, h->stream));
+
+    std::vector<double> fan(L, 0.0);
+    for (int lv = 0; lv < L; lv++) fan[lv] = (double)h->cands[lv].size();
+    long long seq_base = 0;
+    const int P = std::max(1, h->prm.part_count), R = h->prm.part_rank;
+    bool sliced = P <= 1;
+    float ms = 0;
+
+    for (;;) {
+        int lv = -1;
+        if (!sliced) {
+            // breadth-first prologue shared by every part: take whole levels until one is wide
+            // enough to be cut into P contiguous slices of the canonical order.
+            for (int l = 0; l < L; l++) if (h->tail[l] > h->head[l]) { lv = l; break; }
+            if (lv < 0) break;
+            const long long width = h->tail[lv] - h->head[lv];
+            const bool wide = width >= 64ll * P;
+            const bool last = lv == L - 1;
+            const bool risky = lv + 1 < L && (double)width * (double)h->cands[lv].size() > 0.5 * (double)h->cap;
+            if (wide || last || risky) {
+                const long long a = h->head[lv] + width * R / P, b = h->head[lv] + width * (R + 1) / P;
+                h->head[lv] = a;
+                h->tail[lv] = b;
+                sliced = true;
+                if (a == b) break;
+            }
+        } else {
+            for (int l = L - 1; l >= 0; l--) if (h->tail[l] > h->head[l]) { lv = l; break; }
+            if (lv < 0) break;
+        }
+        const long long pending = h->tail[lv] - h->head[lv];
+        const bool leaf = lv == L - 1;
+        long long B = pending;
+        if (B > h->chunk_max) B = h->chunk_max;
+        if (!leaf) {
+            const long long guess = (long long)(0.8 * (double)h->cap / std::max(1.0, fan[lv]));
+            if (B > std::max(1024ll, guess)) B = std::max(1024ll, guess);
+        } else {
+            // every passing choice of the last node may become a candidate: keep them all in d_cands
+            const long long fit = h->cap / std::max<long long>(1, (long long)h->cands[lv].size());
+            if (B > fit) B = std::max(1ll, fit);
+        }
+        const unsigned *items = h->d_level[lv] + (size_t)h->head[lv] * (h->stride >> 2);
+        CK(cudaEventRecord(h->evc0, h->stream));
+        if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        CK(cudaEventRecord(h->evc1, h->stream));
+        const unsigned long long limit = leaf ? ~0ull >> 1 : (unsigned long long)h->cap;
+        if (launch_scan(h, B, limit) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        st.num_launches += 4;
+        if (leaf) {
+            leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem, h->stream>>>(
+                h->net, items, B, h->head[lv], h->d_mask, h->d_off, seq_base, h->prm.max_num_trees, R,
+                h->d_meta, h->prm.num_save, h->d_cands, h->cap);
+            CK(cudaGetLastError());
+            st.num_launches++;
+            if (run_select(h, h->d_level[lv], 0, nullptr, 0, h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            CK(cudaStreamSynchronize(h->stream));
+            const long long total = (long long)h->h_scan->total;
+            st.num_checks += B * (long long)h->cands[lv].size();
+            st.num_grow_calls += total;
+            st.frontier_bytes += B * (long long)h->stride;
+            const long long before = seq_base;
+            seq_base += total;
+            st.num_scored += std::min(seq_base, (long long)h->prm.max_num_trees) - std::min(before, (long long)h->prm.max_num_trees);
+            h->head[lv] += B;
+        } else {
+            if (alloc_level(h, lv + 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            CK(cudaStreamSynchronize(h->stream));
+            const long long n_fit = (long long)(h->h_scan->fit >> 32);
+            const long long total_fit = (long long)(h->h_scan->fit & 0xffffffffull);
+            if (n_fit == 0 && h->h_scan->total > 0) {
+                set_err("level_capacity %lld too small for one item's children", h->cap);
+                return LICHEE_ERR_INVALID;
+            }
+            const long long done = h->h_scan->total <= (unsigned long long)h->cap ? B : n_fit;
+            if (total_fit > 0 || done > 0) {
+                emit_kernel<<<grid_for(done), kThreads, 0, h->stream>>>(h->net, lv, items, done, h->d_mask,
+                                                                        h->d_off, h->d_level[lv + 1]);
+                CK(cudaGetLastError());
+                st.num_launches++;
+            }
+            const long long produced = h->h_scan->total <= (unsigned long long)h->cap ? (long long)h->h_scan->total : total_fit;
+            h->head[lv + 1] = 0;
+            h->tail[lv + 1] = produced;
+            h->head[lv] += done;
+            st.num_checks += done * (long long)h->cands[lv].size();
+            st.num_grow_calls += produced;
+            st.frontier_bytes += (done + produced) * (long long)h->stride;
+            if (done > 0) fan[lv] = 0.5 * fan[lv] + 0.5 * std::max(1.0, (double)produced / (double)done);
+        }
+        CK(cudaEventElapsedTime(&ms, h->evc0, h->evc1));
+        st.kernel_ms_check += ms;
+        if (h->head[lv] == h->tail[lv]) h->head[lv] = h->tail[lv] = 0;
+        if (seq_base >= h->prm.max_num_trees) { st.status |= LICHEE_STATUS_TREE_CAP; break; }
+        if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    st.kernel_ms_total = ms;
+    st.num_trees = std::min(seq_base, (long long)h->prm.max_num_trees);
+    return fetch_top(h);
+}
+
+}  // namespace
+
+extern "C" {
+
+void lichee_default_params(lichee_search_params *p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->vaf_error_margin = 0.1;          // Parameters.VAF_ERROR_MARGIN
+    p->num_save = 1;                    // LineageEngine.Args.numSave
+    p->max_num_trees = 100000;          // Parameters.MAX_NUM_TREES
+    p->max_num_grow_calls = 100000000;  // Parameters.MAX_NUM_GROW_CALLS
+    p->part_rank = 0;
+    p->part_count = 1;
+}
+
+const char *lichee_last_error(void) { return g_err.c_str(); }
+const char *lichee_version(void) { return "lichee_b200 0.1 (sm_100a)"; }
+
+int lichee_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lichee_search_destroy(lichee_search *h) {
+    if (!h) return LICHEE_OK;
+    if (h->stream) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(h->d_vaf); cudaFree(h->d_sigma); cudaFree(h->d_cand); cudaFree(h->d_ncand);
+    for (unsigned *p : h->d_level) cudaFree(p);
+    cudaFree(h->d_mask); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_tile); cudaFree(h->d_scan);
+    if (h->h_scan) cudaFreeHost(h->h_scan);
+    cudaFree(h->d_meta); cudaFree(h->d_cands);
+    cudaFree(h->d_top[0]); cudaFree(h->d_top[1]); cudaFree(h->d_tree[0]); cudaFree(h->d_tree[1]);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evc0) cudaEventDestroy(h->evc0);
+    if (h->evc1) cudaEventDestroy(h->evc1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return LICHEE_OK;
+}
+
+int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_t *adj_off,
+                         const int32_t *adj_idx, const double *vaf, const lichee_search_params *params) {
+    if (!out || !adj_off || !vaf || !params || n < 1 || S < 1 || (!adj_idx && adj_off[n] > 0)) {
+        set_err("lichee_search_create: invalid argument");
+        return LICHEE_ERR_INVALID;
+    }
+    if (n > LICHEE_MAX_NODES || S > LICHEE_MAX_SAMPLES) {
+        set_err("network too large: %d nodes (max %d), %d samples (max %d)", n, LICHEE_MAX_NODES, S, LICHEE_MAX_SAMPLES);
+        return LICHEE_ERR_TOO_LARGE;
+    }
+    if (params->num_save < 1 || params->num_save > LICHEE_MAX_SAVE || params->max_num_trees < 1 ||
+        params->max_num_grow_calls < 1 || params->part_count < 0 || params->part_rank < 0 ||
+        (params->part_count > 0 && params->part_rank >= params->part_count)) {
+        set_err("lichee_search_create: parameter out of range (num_save 1..%d)", LICHEE_MAX_SAVE);
+        return LICHEE_ERR_INVALID;
+    }
+    // parents of every node, ascending id, duplicates removed; DAG test (Kahn)
+    std::vector<std::vector<int>> par(n);
+    std::vector<int> indeg(n, 0);
+    for (int u = 0; u < n; u++) {
+        if (adj_off[u + 1] < adj_off[u]) { set_err("adj_off not monotone"); return LICHEE_ERR_INVALID; }
+        for (int k = adj_off[u]; k < adj_off[u + 1]; k++) {
+            const int v = adj_idx[k];
+            if (v < 0 || v >= n) { set_err("edge target %d out of range", v); return LICHEE_ERR_INVALID; }
+            if (std::find(par[v].begin(), par[v].end(), u) == par[v].end()) par[v].push_back(u);
+        }
+    }
+    for (int v = 0; v < n; v++) { std::sort(par[v].begin(), par[v].end()); indeg[v] = (int)par[v].size(); }
+    {
+        std::vector<int> deg = indeg, q;
+        for (int v = 0; v < n; v++) if (deg[v] == 0) q.push_back(v);
+        size_t qi = 0;
+        while (qi < q.size()) {
+            const int u = q[qi++];
+            for (int k = adj_off[u]; k < adj_off[u + 1]; k++) {
+                const int v = adj_idx[k];
+                // count each distinct edge once
+                bool first = true;
+                for (int k2 = adj_off[u]; k2 < k; k2++) if (adj_idx[k2] == v) first = false;
+                if (first && --deg[v] == 0) q.push_back(v);
+            }
+        }
+        if ((int)q.size() != n) {
+            set_err("constraint network has a directed cycle; the parent-choice search needs a DAG");
+            return LICHEE_ERR_CYCLIC;
+        }
+    }
+    if (lichee_device_count() < 1) {
+        set_err("no CUDA device available: lichee_b200 has no CPU fallback");
+        return LICHEE_ERR_NO_DEVICE;
+    }
+    lichee_search *h = new lichee_search();
+    h->n = n; h->S = S; h->prm = *params;
+    if (h->prm.part_count < 1) { h->prm.part_count = 1; h->prm.part_rank = 0; }
+    h->device = params->device;
+    h->L = n - 1;
+    h->SP = S <= 32 ? 32 : 64;
+    h->stride = std::max(16, ((h->L + 15) / 16) * 16);
+    // a tree exists only if the root has children (PHYNetwork.java:557) and every other node a parent
+    h->no_trees = adj_off[1] == adj_off[0] && n > 1;
+    if (indeg[0] != 0) h->no_trees = true;   // the root must be a source
+    for (int v = 1; v < n; v++) if (par[v].empty()) h->no_trees = true;
+    if (n == 1) h->no_trees = true;          // getLineageTrees returns an empty list
+    // sigma: non-root nodes by descending VAF mass, ties by ascending id
+    std::vector<double> mass(n, 0.0);
+    for (int v = 0; v < n; v++) { double m = 0; for (int s = 0; s < S; s++) m += vaf[(size_t)v * S + s]; mass[v] = m; }
+    h->sigma.resize(h->L);
+    for (int t = 0; t < h->L; t++) h->sigma[t] = t + 1;
+    std::stable_sort(h->sigma.begin(), h->sigma.end(), [&](int a, int b) { return mass[a] > mass[b]; });
+    h->cands.resize(h->L);
+    for (int t = 0; t < h->L; t++) h->cands[t] = par[h->sigma[t]];
+
+#define CKD(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_err("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_));  \
+            lichee_search_destroy(h);                                                              \
+            return LICHEE_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+    CKD(cudaSetDevice(h->device));
+    CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
+    CKD(cudaEventCreate(&h->evc0)); CKD(cudaEventCreate(&h->evc1));
+    const int Lp = std::max(1, h->L);
+    std::vector<double> vp((size_t)n * h->SP, 0.0);
+    for (int v = 0; v < n; v++) for (int s = 0; s < S; s++) vp[(size_t)v * h->SP + s] = vaf[(size_t)v * S + s];
+    std::vector<uint8_t> sg(kMaxN, 0), cd((size_t)Lp * kMaxN, 0), nc(kMaxN, 0);
+    for (int t = 0; t < h->L; t++) {
+        sg[t] = (uint8_t)h->sigma[t];
+        nc[t] = (uint8_t)h->cands[t].size();
+        for (size_t i = 0; i < h->cands[t].size(); i++) cd[(size_t)t * kMaxN + i] = (uint8_t)h->cands[t][i];
+    }
+    CKD(cudaMalloc(&h->d_vaf, vp.size() * sizeof(double)));
+    CKD(cudaMalloc(&h->d_sigma, sg.size()));
+    CKD(cudaMalloc(&h->d_cand, cd.size()));
+    CKD(cudaMalloc(&h->d_ncand, nc.size()));
+    CKD(cudaMemcpyAsync(h->d_vaf, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(h->d_sigma, sg.data(), sg.size(), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(h->d_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(h->d_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
+    h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
+    if (h->cap < 1024) h->cap = 1024;
+    h->chunk_max = std::min<long long>(h->cap, 1ll << 20);
+    h->d_level.assign(Lp, nullptr);
+    h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
+    const long long tiles = (h->cap + kScanTile - 1) / kScanTile + 1;
+    CKD(cudaMalloc(&h->d_mask, sizeof(uint4) * h->chunk_max));
+    CKD(cudaMalloc(&h->d_cnt, sizeof(unsigned) * h->chunk_max));
+    CKD(cudaMalloc(&h->d_off, sizeof(unsigned) * h->chunk_max));
+    CKD(cudaMalloc(&h->d_tile, sizeof(unsigned long long) * tiles));
+    CKD(cudaMalloc(&h->d_scan, sizeof(ScanOut)));
+    CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut)));
+    CKD(cudaMalloc(&h->d_meta, sizeof(TopMeta)));
+    CKD(cudaMalloc(&h->d_cands, sizeof(Cand) * h->cap));
+    for (int i = 0; i < 2; i++) {
+        CKD(cudaMalloc(&h->d_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
+        CKD(cudaMalloc(&h->d_tree[i], (size_t)LICHEE_MAX_SAVE * h->stride));
+    }
+    h->net.vaf = h->d_vaf; h->net.sigma = h->d_sigma; h->net.cand = h->d_cand; h->net.ncand = h->d_ncand;
+    h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
+    h->net.margin = params->vaf_error_margin;
+    h->smem = (size_t)n * h->SP * sizeof(double) + 2 * kMaxN;
+    CKD(cudaFuncSetAttribute(check_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
+    CKD(cudaStreamSynchronize(h->stream));
+#undef CKD
+    *out = h;
+    return LICHEE_OK;
+}
+
+int lichee_search_run(lichee_search *h) {
+    if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const int rc = h->SP == 32 ? run_search<1>(h) : run_search<2>(h);
+    if (rc == LICHEE_OK) h->ran = true;
+    return rc;
+}
+
+int lichee_search_get_stats(const lichee_search *h, lichee_search_stats *out) {
+    if (!h || !out) { set_err("null argument"); return LICHEE_ERR_INVALID; }
+    if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
+    *out = h->stats;
+    return LICHEE_OK;
+}
+
+int lichee_search_get_order(const lichee_search *h, int32_t *sigma) {
+    if (!h || !sigma) { set_err("null argument"); return LICHEE_ERR_INVALID; }
+    for (int t = 0; t < h->L; t++) sigma[t] = h->sigma[t];
+    return LICHEE_OK;
+}
+
+int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int32_t *parent,
+                           int32_t *order, int64_t *seq) {
+    if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
+    if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
+    if (k < 0 || (size_t)k >= h->h_top.size()) { set_err("tree index %d out of range", k); return LICHEE_ERR_INVALID; }
+    if (score) *score = h->h_top[k].score;
+    if (seq) *seq = h->h_top[k].seq;
+    const uint8_t *b = h->h_tree.data() + (size_t)k * h->stride;
+    if (parent) {
+        parent[0] = -1;
+        for (int t = 0; t < h->L; t++) parent[h->sigma[t]] = b[t];
+    }
+    if (order) {
+        // treeNodes: root first, then a preorder in which a node always follows its parent and the
+        // children of one parent keep the canonical (sigma) order used for the sums.
+        std::vector<std::vector<int>> ch(h->n);
+        for (int t = 0; t < h->L; t++) ch[b[t]].push_back(h->sigma[t]);
+        std::vector<int> stack{0};
+        int w = 0;
+        while (!stack.empty()) {
+            const int u = stack.back();
+            stack.pop_back();
+            order[w++] = u;
+            for (auto it = ch[u].rbegin(); it != ch[u].rend(); ++it) stack.push_back(*it);
+        }
+        for (; w < h->n; w++) order[w] = -1;
+    }
+    return LICHEE_OK;
+}
+
+int64_t lichee_record_bytes(const lichee_search *h) { return h ? 24 + h->stride : 0; }
+
+int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_ptr) {
+    if (!h || !dst) { set_err("null argument"); return LICHEE_ERR_INVALID; }
+    if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
+    CK(cudaSetDevice(h->device));
+    const long long rb = 24 + h->stride;
+    unsigned char *d = nullptr;
+    if (device_ptr) d = static_cast<unsigned char *>(dst);
+    else CK(cudaMalloc(&d, (size_t)rb * h->prm.num_save));
+    export_records<<<h->prm.num_save, 32, 0, h->stream>>>(h->d_meta, h->d_top[h->flip], h->d_tree[h->flip],
+                                                          h->stride >> 2, h->prm.num_save, d, rb);
+    CK(cudaGetLastError());
+    if (!device_ptr) {
+        CK(cudaMemcpyAsync(dst, d, (size_t)rb * h->prm.num_save, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(d);
+    } else {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return LICHEE_OK;
+}
+
+int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_lists, int device_ptr) {
+    if (!h || !records || n_lists < 1) { set_err("invalid argument"); return LICHEE_ERR_INVALID; }
+    if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
+    CK(cudaSetDevice(h->device));
+    const long long rb = 24 + h->stride;
+    const long long n = (long long)n_lists * h->prm.num_save;
+    if (n > h->cap) { set_err("too many records to merge"); return LICHEE_ERR_INVALID; }
+    const unsigned char *d = static_cast<const unsigned char *>(records);
+    unsigned char *tmp = nullptr;
+    if (!device_ptr) {
+        CK(cudaMalloc(&tmp, (size_t)rb * n));
+        CK(cudaMemcpyAsync(tmp, records, (size_t)rb * n, cudaMemcpyHostToDevice, h->stream));
+        d = tmp;
+    }
+    records_to_cands<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(d, rb, n, h->d_cands, h->d_meta);
+    CK(cudaGetLastError());
+    if (run_select(h, nullptr, 1, d, rb, h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+    const int rc = fetch_top(h);
+    if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+int lichee_get_lineage_trees(int32_t n, int32_t S, const int32_t *adj_off, const int32_t *adj_idx,
+                             const double *vaf, const lichee_search_params *params,
+                             lichee_search_stats *stats, double *scores, int32_t *parents, int32_t *orders) {
+    lichee_search *h = nullptr;
+    int rc = lichee_search_create(&h, n, S, adj_off, adj_idx, vaf, params);
+    if (rc != LICHEE_OK) return rc;
+    rc = lichee_search_run(h);
+    if (rc == LICHEE_OK) {
+        if (stats) *stats = h->stats;
+        for (uint32_t k = 0; k < h->stats.num_saved && rc == LICHEE_OK; k++)
+            rc = lichee_search_get_tree(h, (int32_t)k, scores ? scores + k : nullptr,
+                                        parents ? parents + (size_t)k * n : nullptr,
+                                        orders ? orders + (size_t)k * n : nullptr, nullptr);
+    }
+    lichee_search_destroy(h);
+    return rc;
+}
+
+}  // extern "C"

@@ -70,3 +70,24 @@ def search(adj, vaf, margin, top_s=1, max_trees=100000, max_grow=100000000, mode
         out["all_scores"] = alls[:k]
         out["all_parents"] = allp[:k]
     return out
+
+
+def canonical_search(adj, vaf, margin, top_s=1, max_trees=100000):
+    """Sequential statement of the device's canonical enumeration order (see lichee_oracle.c)."""
+    lib = _load()
+    vaf = np.ascontiguousarray(vaf, dtype=np.float64)
+    n, S = vaf.shape
+    off, idx = to_csr(adj)
+    sc = np.zeros(max(top_s, 1), dtype=np.float64)
+    par = np.full((max(top_s, 1), n), -1, dtype=np.int32)
+    seq = np.zeros(max(top_s, 1), dtype=np.int64)
+    stats = np.zeros(3, dtype=np.int64)
+    sigma = np.zeros(max(n - 1, 1), dtype=np.int32)
+    P = ctypes.c_void_p
+    lib.lichee_canonical_search(
+        ctypes.c_int(n), ctypes.c_int(S), P(off.ctypes.data), P(idx.ctypes.data), P(vaf.ctypes.data),
+        ctypes.c_double(margin), ctypes.c_long(max_trees), ctypes.c_int(top_s), P(sc.ctypes.data),
+        P(par.ctypes.data), P(seq.ctypes.data), P(stats.ctypes.data), P(sigma.ctypes.data))
+    m = int(min(stats[0], top_s))
+    return dict(scores=sc[:m], parents=par[:m], seq=seq[:m], n_trees=int(stats[0]), n_grow=int(stats[1]),
+                n_checks=int(stats[2]), sigma=sigma[:n - 1])

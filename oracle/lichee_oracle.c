@@ -298,3 +298,111 @@ int lichee_oracle_search(int n, int S, const int *adj_off, const int *adj_idx, c
     free(s.res_nodes); free(s.res_parent); free(s.res_has); free(r); free(tmp);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Canonical-order specification (TEST INFRASTRUCTURE): a sequential statement of the order in
+ * which lichee_b200 enumerates and sums, used to check the CUDA path bit for bit.  The SET of
+ * valid trees and every tree's score are the reference's (up to the floating-point effect of the
+ * child summation order); only the enumeration order differs -- DESIGN.md "enumeration order"
+ * explains why the reference's own order cannot be reproduced by any parallel search.
+ *
+ *   sigma   : non-root nodes by descending sum of VAF over samples, ties by ascending id
+ *   tree    : one parent per node, parents of a node taken in ascending id
+ *   order   : lexicographic in (parent of sigma[0], parent of sigma[1], ...)
+ *   sums    : children of a parent are added in sigma order (checkConstraint, PHYTree.java:156-174,
+ *             and computeErrorScore, PHYTree.java:214-233, with that child list order)
+ *   caps    : the first max_trees valid trees in this order
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n, S, L; const double *vaf; double margin; long max_trees;
+    int *sigma; int **cand; int *ncand;
+    int *par;                   /* parent of sigma[t] */
+    int **ch; int *nch;         /* children per parent, in sigma order */
+    long n_trees, n_checks, n_grow;
+    int top_s; long kept; double *k_score; long *k_seq; int *k_par;  /* ranked list, insertion sort */
+} canon_t;
+
+static double canon_score(canon_t *c) {
+    double err = 0;
+    for (int p = c->n - 1; p >= 0; p--) {
+        if (c->nch[p] == 0) continue;
+        for (int i = 0; i < c->S; i++) {
+            double sum = 0;
+            for (int k = 0; k < c->nch[p]; k++) sum += c->vaf[(size_t)c->ch[p][k] * c->S + i];
+            double a = c->vaf[(size_t)p * c->S + i];
+            if (sum > a) err += (sum - a) * (sum - a);
+        }
+    }
+    return sqrt(err);
+}
+static void canon_keep(canon_t *c, double score, long seq) {
+    if (c->kept == c->top_s && !(score < c->k_score[c->kept - 1])) return;
+    long pos = c->kept < c->top_s ? c->kept : c->kept - 1;
+    while (pos > 0 && score < c->k_score[pos - 1]) {
+        c->k_score[pos] = c->k_score[pos - 1]; c->k_seq[pos] = c->k_seq[pos - 1];
+        memcpy(c->k_par + pos * c->n, c->k_par + (pos - 1) * c->n, sizeof(int) * c->n);
+        pos--;
+    }
+    c->k_score[pos] = score; c->k_seq[pos] = seq;
+    c->k_par[pos * c->n] = -1;
+    for (int t = 0; t < c->L; t++) c->k_par[pos * c->n + c->sigma[t]] = c->par[t];
+    if (c->kept < c->top_s) c->kept++;
+}
+static void canon_rec(canon_t *c, int t) {
+    c->n_grow++;
+    if (t == c->L) { if (c->n_trees < c->max_trees) { canon_keep(c, canon_score(c), c->n_trees); } c->n_trees++; return; }
+    int v = c->sigma[t];
+    for (int i = 0; i < c->ncand[t] && c->n_trees < c->max_trees; i++) {
+        int p = c->cand[t][i], ok = 1;
+        c->n_checks++;
+        c->ch[p][c->nch[p]++] = v;
+        for (int s = 0; s < c->S && ok; s++) {
+            double sum = 0;
+            for (int k = 0; k < c->nch[p]; k++) sum += c->vaf[(size_t)c->ch[p][k] * c->S + s];
+            if (sum > c->vaf[(size_t)p * c->S + s] + c->margin) ok = 0;
+        }
+        if (ok) { c->par[t] = p; canon_rec(c, t + 1); }
+        c->nch[p]--;
+    }
+}
+/* stats: [0] valid trees (capped), [1] grow calls, [2] checks.  out_sigma[n-1]. */
+int lichee_canonical_search(int n, int S, const int *adj_off, const int *adj_idx, const double *vaf,
+                            double margin, long max_trees, int top_s, double *out_score, int *out_parent,
+                            long *out_seq, long *stats, int *out_sigma) {
+    canon_t c; memset(&c, 0, sizeof(c));
+    c.n = n; c.S = S; c.L = n - 1; c.vaf = vaf; c.margin = margin; c.max_trees = max_trees; c.top_s = top_s;
+    c.sigma = (int *)malloc(sizeof(int) * (n + 1)); c.par = (int *)malloc(sizeof(int) * (n + 1));
+    c.cand = (int **)malloc(sizeof(int *) * (n + 1)); c.ncand = (int *)calloc(n + 1, sizeof(int));
+    c.ch = (int **)malloc(sizeof(int *) * n); c.nch = (int *)calloc(n, sizeof(int));
+    double *mass = (double *)calloc(n, sizeof(double));
+    for (int v = 0; v < n; v++) { c.ch[v] = (int *)malloc(sizeof(int) * (n + 1)); for (int s = 0; s < S; s++) mass[v] += vaf[(size_t)v * S + s]; }
+    for (int t = 0; t < c.L; t++) c.sigma[t] = t + 1;
+    for (int i = 1; i < c.L; i++) {                     /* stable insertion sort, descending mass */
+        int x = c.sigma[i], j = i;
+        while (j > 0 && mass[c.sigma[j - 1]] < mass[x]) { c.sigma[j] = c.sigma[j - 1]; j--; }
+        c.sigma[j] = x;
+    }
+    int feasible = n > 1 && adj_off[1] > adj_off[0];
+    for (int k = 0; k < adj_off[n]; k++) if (adj_idx[k] == 0) feasible = 0;
+    for (int t = 0; t < c.L; t++) {
+        int v = c.sigma[t];
+        c.cand[t] = (int *)malloc(sizeof(int) * (n + 1));
+        for (int u = 0; u < n; u++) {                   /* ascending id, duplicates collapse */
+            int has = 0;
+            for (int k = adj_off[u]; k < adj_off[u + 1]; k++) if (adj_idx[k] == v) has = 1;
+            if (has) c.cand[t][c.ncand[t]++] = u;
+        }
+        if (c.ncand[t] == 0) feasible = 0;
+        if (out_sigma) out_sigma[t] = v;
+    }
+    c.k_score = (double *)malloc(sizeof(double) * (top_s + 1)); c.k_seq = (long *)malloc(sizeof(long) * (top_s + 1));
+    c.k_par = (int *)malloc(sizeof(int) * (size_t)(top_s + 1) * n);
+    if (feasible) canon_rec(&c, 0); else c.n_grow = 1;
+    for (long k = 0; k < c.kept; k++) { out_score[k] = c.k_score[k]; out_seq[k] = c.k_seq[k]; memcpy(out_parent + k * n, c.k_par + k * n, sizeof(int) * n); }
+    stats[0] = c.n_trees < max_trees ? c.n_trees : max_trees; stats[1] = c.n_grow; stats[2] = c.n_checks;
+    for (int t = 0; t < c.L; t++) free(c.cand[t]);
+    for (int v = 0; v < n; v++) free(c.ch[v]);
+    free(c.sigma); free(c.par); free(c.cand); free(c.ncand); free(c.ch); free(c.nch); free(mass);
+    free(c.k_score); free(c.k_seq); free(c.k_par);
+    return 0;
+}

@@ -1,0 +1,182 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Two layers, both from oracle/lichee_oracle.c:
+  * canonical_search  -- sequential statement of the device's enumeration/summation order:
+                         compared BIT FOR BIT (tree count, ranked trees, scores, seq numbers).
+  * search (mode 0)   -- the reference's own Gabow-Myers search, restated literally: compared on
+                         everything that does not depend on its history-dependent enumeration
+                         order: the SET of valid trees, each tree's score (<= 1e-9 relative, the
+                         tolerance BASELINE.json states), the ranked score list, and the ranked
+                         trees themselves whenever scores are distinct.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.synth import make_instance
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+
+
+def rand_dag(rng, n, S, p_edge, vaf_scale):
+    order = list(range(1, n)); rng.shuffle(order); order = [0] + order
+    rank = {v: i for i, v in enumerate(order)}
+    adj = [[] for _ in range(n)]
+    for i in range(n):
+        for j in range(i + 1, n):
+            if rng.random() < p_edge:
+                adj[order[i]].append(order[j])
+    for v in range(1, n):
+        if not any(v in a for a in adj):
+            adj[order[rng.randrange(rank[v])]].append(v)
+    for a in adj:
+        rng.shuffle(a)
+    vaf = np.array([[0.5] * S] + [[rng.random() * vaf_scale for _ in range(S)] for _ in range(n - 1)])
+    return adj, vaf
+
+
+def gpu_search(adj, vaf, margin, num_save, **kw):
+    import lichee_b200
+    s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=num_save, **kw)
+    try:
+        st = s.run()
+        return st.as_dict(), s.trees(), list(s.sigma())
+    finally:
+        s.close()
+
+
+def assert_matches_canonical(adj, vaf, margin, num_save, max_trees=10**9, **kw):
+    st, trees, sigma = gpu_search(adj, vaf, margin, num_save, max_num_trees=max_trees, **kw)
+    ref = oracle.canonical_search(adj, vaf, margin, top_s=num_save, max_trees=max_trees)
+    assert sigma == list(ref["sigma"])
+    assert st["num_trees"] == ref["n_trees"]
+    assert len(trees) == len(ref["scores"])
+    for k, t in enumerate(trees):
+        assert t.errorScore == ref["scores"][k], (k, t.errorScore, ref["scores"][k])   # bit-exact double
+        assert t.parent == list(ref["parents"][k]), k
+        assert t.seq == ref["seq"][k], k
+    if not (st["status"] & 3):
+        assert st["num_checks"] == ref["n_checks"]
+        assert st["num_grow_calls"] == ref["n_grow"]
+    return st, trees, ref
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_dags_bit_exact_vs_canonical(built, seed):
+    rng = random.Random(seed)
+    n = rng.randint(2, 11); S = rng.randint(1, 6)
+    adj, vaf = rand_dag(rng, n, S, rng.choice([0.3, 0.6, 0.9]), rng.choice([0.15, 0.3, 0.5]))
+    assert_matches_canonical(adj, vaf, 0.1, num_save=rng.choice([1, 7, 100]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_synthetic_complete_network_vs_canonical(built, seed):
+    net, prm = make_instance(11, 5, seed)
+    st, trees, ref = assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=100, max_trees=300000)
+    assert st["num_trees"] > 0
+
+
+def test_more_than_32_samples_two_per_lane(built):
+    net, prm = make_instance(12, 40, seed=5)
+    assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=50, max_trees=200000)
+    net, prm = make_instance(14, 64, seed=6)
+    assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=1000, max_trees=100000)
+
+
+def test_chunked_frontier_small_level_capacity(built):
+    """A tiny level_capacity forces many depth-first chunks and partial emits; results must not move."""
+    net, prm = make_instance(11, 4, seed=2)
+    a = assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=64, max_trees=10**9)[0]
+    b = assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=64, max_trees=10**9,
+                                 level_capacity=1024)[0]
+    assert a["num_trees"] == b["num_trees"] and b["num_launches"] > a["num_launches"]
+
+
+def test_tree_cap_is_a_prefix_of_the_canonical_order(built):
+    """Parameters.MAX_NUM_TREES: the first max_trees valid trees in enumeration order are kept."""
+    net, prm = make_instance(12, 4, seed=1)
+    for cap in (1, 17, 1000, 100000):
+        st, trees, ref = assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=10, max_trees=cap)
+        assert st["num_trees"] <= cap
+        if st["num_trees"] == cap:
+            assert st["status"] & 1
+            assert all(t.seq < cap for t in trees)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_valid_tree_set_and_scores_vs_reference_search(built, seed):
+    """Against the literal restatement of PHYNetwork.grow: same set of valid trees, same scores
+    (1e-9 relative), same ranked score list; identical ranked trees where scores are distinct."""
+    rng = random.Random(100 + seed)
+    if seed % 2:
+        net, prm = make_instance(8, 3, seed)
+        adj, vaf, margin = net.adj, np.array(net.aaf), prm.vaf_error_margin
+    else:
+        n = rng.randint(3, 9); S = rng.randint(1, 4)
+        adj, vaf = rand_dag(rng, n, S, rng.choice([0.4, 0.8]), rng.choice([0.2, 0.4]))
+        margin = 0.1
+    ref = oracle.search(adj, vaf, margin, top_s=1024, max_trees=10**7, want_all=10**6)
+    st, trees, _ = gpu_search(adj, vaf, margin, 1024, max_num_trees=10**9)
+    assert st["num_trees"] == ref["n_trees"]
+    ref_by_tree = {bytes(np.asarray(p, dtype=np.int32)): s for p, s in zip(ref["all_parents"], ref["all_scores"])}
+    assert len(ref_by_tree) == ref["n_trees"]
+    for k, t in enumerate(trees):
+        key = bytes(np.asarray(t.parent, dtype=np.int32))
+        assert key in ref_by_tree
+        assert abs(ref_by_tree[key] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
+        assert abs(ref["scores"][k] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
+    # where neighbouring reference scores differ by more than the tolerance the ranked trees are identical
+    rs = ref["scores"]
+    for k, t in enumerate(trees):
+        lo = k == 0 or rs[k] - rs[k - 1] > 1e-7 * max(rs[k], 1e-12)
+        hi = k + 1 >= len(rs) or rs[k + 1] - rs[k] > 1e-7 * max(rs[k], 1e-12)
+        if lo and hi and len(trees) == st["num_trees"]:
+            assert t.parent == list(ref["parents"][k])
+
+
+def test_edge_cases(built):
+    import lichee_b200
+    # root only: getLineageTrees returns an empty list (PHYNetwork.java:557)
+    st, trees, _ = gpu_search([[]], np.array([[0.5]]), 0.1, 1)
+    assert st["num_trees"] == 0 and trees == []
+    # a node no edge reaches: no spanning tree
+    st, trees, _ = gpu_search([[1], [], []], np.array([[0.5], [0.2], [0.1]]), 0.1, 1)
+    assert st["num_trees"] == 0
+    # single chain
+    st, trees, _ = gpu_search([[1], [2], []], np.array([[0.5], [0.3], [0.2]]), 0.1, 5)
+    assert st["num_trees"] == 1 and trees[0].parent == [-1, 0, 1] and trees[0].errorScore == 0.0
+    # every tree violates the sum rule: zero valid trees
+    st, trees, _ = gpu_search([[1, 2], [], []], np.array([[0.5], [0.45], [0.45]]), 0.1, 5)
+    assert st["num_trees"] == 0
+    # duplicate edges collapse (PHYNetwork.addEdge refuses duplicates)
+    st, trees, _ = gpu_search([[1, 1, 2], [2], []], np.array([[0.5], [0.3], [0.2]]), 0.1, 5)
+    assert st["num_trees"] == 2
+    # a directed cycle is rejected
+    with pytest.raises(lichee_b200.LicheeError) as e:
+        gpu_search([[1], [2], [1]], np.array([[0.5], [0.3], [0.2]]), 0.1, 1)
+    assert e.value.code == -3
+    with pytest.raises(lichee_b200.LicheeError):
+        gpu_search([[1], []], np.zeros((2, 65)), 0.1, 1)
+
+
+def test_sharded_search_merges_to_the_single_gpu_answer(built):
+    """part_rank/part_count slices of the canonical order, merged like the NCCL allgather does."""
+    import lichee_b200
+    net, prm = make_instance(11, 5, seed=4)
+    whole, trees, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 32, max_num_trees=10**9)
+    for P in (2, 3, 8):
+        parts = [lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=32, max_num_trees=10**9,
+                                           part_rank=r, part_count=P) for r in range(P)]
+        stats = [p.run() for p in parts]
+        assert sum(s.num_trees for s in stats) == whole["num_trees"]
+        recs = np.concatenate([p.export_ranked() for p in parts])
+        parts[0].merge_ranked(recs, P)
+        merged = parts[0].trees()
+        assert [t.parent for t in merged] == [t.parent for t in trees]
+        assert [t.errorScore for t in merged] == [t.errorScore for t in trees]
+        for p in parts:
+            p.close()
