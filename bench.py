@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- candidate lineage trees checked+scored per second on the headline workload.
+
+Workload (BASELINE.json configs[4], the largest single-GPU configuration and the one the
+north-star speed-up is quoted on): synthetic 64-sample, 120-cluster constraint network built with
+the reference's own edge rule under -c (complete edges), -minClusterSize 1, -e 0.1, -s 1000.
+One "step" = one whole tree search of that network: enumerate spanning trees in canonical order,
+sum-rule check every candidate extension, score every complete valid tree, keep the top 1000.
+Parameters.MAX_NUM_TREES is raised from the reference's 100000 to --max-trees so that a step is
+long enough to measure a B200 (with the reference's default a step is ~10 ms of launch latency).
+
+  value : candidate extensions checked per second, whole job, network already resident in HBM
+  e2e   : same, through the public API with HOST buffers: create (H2D) + run + ranked trees D2H
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
+
+N > 1 (torchrun, one rank per GPU): the frontier is cut at the first tree levels into N contiguous
+slices of the canonical order, each rank searches its slice (the tree cap applies per slice, so
+per-GPU work is fixed: weak scaling) and the N ranked lists are merged with one NCCL all_gather.
+
+--impl reference: the literal CPU port of the reference search (oracle/, the JVM is absent from
+this image) on the same network, each step a bounded sample of grow() calls.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "synthetic 64-sample 120-cluster complete network (-c, -minClusterSize 1, -e 0.1, -s 1000)"
+
+
+def make_workload(args):
+    from lichee_b200.synth import make_instance
+    net, prm = make_instance(args.clusters, args.samples, seed=args.seed)
+    return net.adj, np.ascontiguousarray(net.aaf, dtype=np.float64), prm.vaf_error_margin, net.num_edges
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference(args):
+    """Reference arm: literal CPU port of PHYNetwork.grow on the box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    adj, vaf, margin, n_edges = make_workload(args)
+    sample_grow = args.ref_grow_calls
+    def step():
+        t0 = time.perf_counter()
+        r = oracle.search(adj, vaf, margin, top_s=args.save, max_trees=100000, max_grow=sample_grow, mode=0)
+        return time.perf_counter() - t0, r
+    for _ in range(args.warmup):
+        step()
+    tot_t = tot_c = 0
+    for _ in range(args.steps):
+        dt, r = step()
+        tot_t += dt; tot_c += r["n_checks"]
+    val = tot_c / tot_t
+    line = {
+        "impl": "reference", "metric": "candidate lineage trees checked+scored per second", "value": val,
+        "unit": "candidate trees/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clusters": args.clusters, "samples": args.samples, "edges": n_edges,
+                   "seed": args.seed, "num_save": args.save},
+        "cpu_baseline": {"value": val, "unit": "candidate trees/s", "cores": 1, "kind": "port",
+                         "sample": f"first {sample_grow} grow() calls of the reference's Gabow-Myers search per step "
+                                   f"(literal C port of PHYNetwork.grow; the search is single-threaded in the reference; no JVM in this image)"},
+        "e2e": {"value": val, "unit": "candidate trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clusters", type=int, default=120)
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--save", type=int, default=1000)
+    ap.add_argument("--max-trees", type=int, default=1 << 26)
+    ap.add_argument("--level-capacity", type=int, default=0)
+    ap.add_argument("--ref-grow-calls", type=int, default=1500000)
+    ap.add_argument("--cpu-baseline-grow-calls", type=int, default=5000000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import lichee_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lichee_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    adj, vaf, margin, n_edges = make_workload(args)
+    kw = dict(num_save=args.save, max_num_trees=args.max_trees, max_num_grow_calls=1 << 62, device=local,
+              part_rank=rank, part_count=world, level_capacity=args.level_capacity)
+
+    # pinned host staging of the step's inputs (the arrays the Java host would hand over)
+    off = np.zeros(len(adj) + 1, dtype=np.int32)
+    for i, a in enumerate(adj):
+        off[i + 1] = off[i] + len(a)
+    idx = np.array([c for a in adj for c in a], dtype=np.int32)
+    h2d_bytes = vaf.nbytes + off.nbytes + idx.nbytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    resident = lichee_b200.LineageSearch(adj, vaf, margin, **kw)
+    rb = resident.record_bytes()
+    gather_in = torch.empty(rb * args.save, dtype=torch.uint8, device="cuda")
+    gather_out = torch.empty(world * rb * args.save, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def merge(search):
+        if world > 1:
+            search.export_ranked(gather_in.data_ptr())
+            dist.all_gather_into_tensor(gather_out, gather_in)
+            torch.cuda.synchronize()
+            search.merge_ranked(gather_out.data_ptr(), world, device_ptr=True)
+
+    def step_resident():
+        st = resident.run()
+        merge(resident)
+        return st
+
+    def step_e2e():
+        s = lichee_b200.LineageSearch(adj, vaf, margin, **kw)          # H2D of the network
+        st = s.run()
+        merge(s)
+        trees = s.trees()                                               # D2H of the ranked list
+        s.close()
+        return st, trees
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    stats = [step_resident() for _ in range(args.steps)]
+    barrier()
+    t_dev = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_out = [step_e2e() for _ in range(args.steps)]
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    checks = sum(s.num_checks for s in stats)
+    scored = sum(s.num_scored for s in stats)
+    launches = sum(s.num_launches for s in stats) + (args.steps * 3 if world > 1 else 0)
+    agg = torch.tensor([float(checks), float(scored), float(launches), float(sum(s.num_checks for s, _ in e2e_out))],
+                       dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    checks_all, scored_all, launches_all, e2e_checks_all = [float(x) for x in agg.tolist()]
+    t_dev, t_e2e = [float(x) for x in tmax.tolist()]
+
+    if rank == 0:
+        K = lichee_b200.SearchStats.KERNELS
+        ms = [sum(s.kernel_ms[i] for s in stats) for i in range(5)]
+        nl = [sum(s.kernel_launches[i] for s in stats) for i in range(5)]
+        by = [sum(s.kernel_bytes[i] for s in stats) for i in range(5)]
+        dom = max(range(5), key=lambda i: ms[i])
+        peak, peak_src = measured_peak()
+        achieved = by[dom] / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(K[dom])
+            except Exception:
+                traffic = None
+        st0 = stats[-1]
+        d2h_bytes = len(e2e_out[-1][1]) * (8 + 8 + 2 * 4 * (args.clusters + 1)) + 256
+        line = {
+            "metric": "candidate lineage trees checked+scored per second", "value": checks_all / t_dev,
+            "unit": "candidate trees/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clusters": args.clusters, "samples": args.samples, "edges": n_edges,
+                       "seed": args.seed, "num_save": args.save, "max_num_trees_per_gpu": args.max_trees,
+                       "parallelism": f"frontier slices x{world}" if world > 1 else "single GPU",
+                       "l2": "frontier chunks are produced and consumed once per step; every level buffer is rewritten "
+                             "between timed steps (working set of a step > 126 MB L2)",
+                       "valid_trees_per_step": st0.num_trees * world if world > 1 else st0.num_trees,
+                       "complete_trees_scored_per_s": scored_all / t_dev},
+            "e2e": {"value": e2e_checks_all / t_e2e, "unit": "candidate trees/s", "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": K[dom] + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "launches": nl[dom], "avg_launch_ms": ms[dom] / max(nl[dom], 1),
+                         "algorithmic_bytes_per_launch": by[dom] / max(nl[dom], 1),
+                         "note": "integer/byte frontier work; the kernel is issue-bound, see profiles/"},
+            "kernel_ms_per_step": {K[i]: ms[i] / args.steps for i in range(5)},
+            "kernel_launches_per_step": {K[i]: nl[i] / args.steps for i in range(5)},
+            "device_ms_per_step": sum(s.kernel_ms_total for s in stats) / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            t0 = time.perf_counter()
+            r = oracle.search(adj, vaf, margin, top_s=args.save, max_trees=100000, max_grow=args.cpu_baseline_grow_calls, mode=0)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": r["n_checks"] / dt, "unit": "candidate trees/s", "cores": 1, "kind": "port",
+                "seconds": dt, "valid_trees_found": r["n_trees"],
+                "sample": f"first {args.cpu_baseline_grow_calls} grow() calls of the reference's Gabow-Myers search on the same "
+                          f"network (literal C port of PHYNetwork.grow/PHYTree.checkConstraint; single-threaded like the reference)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

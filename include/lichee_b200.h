@@ -44,6 +44,13 @@ extern "C" {
 #define LICHEE_STATUS_TREE_CAP   1u   /* stopped at max_num_trees   (Parameters.MAX_NUM_TREES)      */
 #define LICHEE_STATUS_GROW_CAP   2u   /* stopped at max_num_grow_calls (Parameters.MAX_NUM_GROW_CALLS) */
 
+#define LICHEE_K_CHECK   0        /* sum-rule check of every candidate extension             */
+#define LICHEE_K_SCAN    1        /* ordered exclusive scan of the pass counts                */
+#define LICHEE_K_EMIT    2        /* write surviving children to the next frontier level      */
+#define LICHEE_K_LEAF    3        /* error score of complete trees + threshold filter         */
+#define LICHEE_K_SELECT  4        /* block-level bitonic top-s selection                      */
+#define LICHEE_NUM_KERNELS 5
+
 typedef struct lichee_search lichee_search;   /* opaque handle: one constraint network on one GPU */
 
 /* Search parameters.  Field <-> reference parameter:
@@ -77,8 +84,12 @@ typedef struct lichee_search_stats {
     int64_t num_scored;          /* complete trees scored                                       */
     int64_t num_launches;        /* kernels launched by lichee_search_run                       */
     int64_t frontier_bytes;      /* algorithmic HBM bytes moved through the frontier buffers    */
-    double  kernel_ms_check;     /* summed CUDA-event time of the sum-rule check kernel         */
     double  kernel_ms_total;     /* CUDA-event time of the whole device search                  */
+    /* per kernel class (LICHEE_K_*): summed CUDA-event time on the launching stream, launches,
+     * and ALGORITHMIC bytes (frontier items + masks each launch must read and write once)       */
+    double  kernel_ms[LICHEE_NUM_KERNELS];
+    int64_t kernel_launches[LICHEE_NUM_KERNELS];
+    int64_t kernel_bytes[LICHEE_NUM_KERNELS];
     uint32_t status;
     uint32_t num_saved;          /* trees held in the ranked list, <= num_save                  */
 } lichee_search_stats;

@@ -46,11 +46,18 @@ class SearchStats(ctypes.Structure):
     _fields_ = [("num_trees", ctypes.c_int64), ("num_grow_calls", ctypes.c_int64),
                 ("num_checks", ctypes.c_int64), ("num_scored", ctypes.c_int64),
                 ("num_launches", ctypes.c_int64), ("frontier_bytes", ctypes.c_int64),
-                ("kernel_ms_check", ctypes.c_double), ("kernel_ms_total", ctypes.c_double),
+                ("kernel_ms_total", ctypes.c_double), ("kernel_ms", ctypes.c_double * 5),
+                ("kernel_launches", ctypes.c_int64 * 5), ("kernel_bytes", ctypes.c_int64 * 5),
                 ("status", ctypes.c_uint32), ("num_saved", ctypes.c_uint32)]
 
+    KERNELS = ("check", "scan", "emit", "leaf", "select")
+
     def as_dict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_}
+        d = {}
+        for f, _ in self._fields_:
+            v = getattr(self, f)
+            d[f] = list(v) if hasattr(v, "__len__") else v
+        return d
 
 
 _lib = None

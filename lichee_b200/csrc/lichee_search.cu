@@ -30,6 +30,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -307,12 +309,39 @@ emit_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel 4: score complete trees.  One warp per leaf-parent item; every passing choice for the
-// last node is a complete valid tree.  Error score = sqrt( sum over parents (descending id) and
-// samples (ascending) of max(0, sum(children) - VAF(parent))^2 ), accumulated in exactly that
-// order like PHYTree.computeErrorScore.  Trees that beat the current threshold are appended to
-// the candidate list.
+// kernel 4: score complete trees.  One warp per leaf-parent item (every node placed but the last);
+// every passing choice p* for the last node is a complete valid tree.
+//   score = sqrt( sum over parents p, samples s of max(0, sum(children of p)[s] - VAF(p)[s])^2 )
+// (PHYTree.computeErrorScore, PHYTree.java:214-233).  The reference adds the positive terms one
+// after another; with noisy centroids a tree has thousands of them, i.e. thousands of dependent
+// double additions per tree.  The device uses a FIXED-SHAPE reduction instead (documented in
+// DESIGN.md "accumulation order", restated on the CPU by lichee_canonical_search):
+//   E[p]  = butterfly over the 32 lanes of ( t[p][lane] + t[p][lane+32] )      t = positive term or 0
+//   total = butterfly over the 32 lanes of ( (E[lane]+E[lane+32]) + (E[lane+64]+E[lane+96]) )
+// The shape does not depend on the tree, so trees with the same terms get bit-equal scores, the
+// result is within a few ulp of the reference's sequential sum (tolerance 1e-9), and all trees of
+// one item share every E[p] except E[p*]: O(log n) work per tree.
+// Trees that beat the current s-th best score are appended to the candidate list.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double butterfly_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+
+template <int SPL>
+__device__ __forceinline__ double parent_excess(double s0, double s1, double a0, double a1, bool valid0,
+                                                bool valid1) {
+    const double d0 = __dsub_rn(s0, a0);
+    double t = (valid0 && s0 > a0) ? __dmul_rn(d0, d0) : 0.0;
+    if (SPL == 2) {
+        const double d1 = __dsub_rn(s1, a1);
+        const double t1 = (valid1 && s1 > a1) ? __dmul_rn(d1, d1) : 0.0;
+        t = __dadd_rn(t, t1);
+    }
+    return butterfly_sum(t);
+}
+
 template <int SPL>
 __global__ void __launch_bounds__(kThreads)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, long long item_base,
@@ -331,7 +360,9 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const int wstride = net.stride >> 2;
-    const int wl = level >> 2, sh = 8 * (level & 3);
+    const int v = sigma_s[level];
+    const double xv0 = vaf_s[v * SP + lane];
+    const double xv1 = SPL == 2 ? vaf_s[v * SP + 32 + lane] : 0.0;
     const double tau = meta->tau;
     const bool full = meta->count >= (unsigned)num_save;
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -340,8 +371,26 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     for (long long it = warp0; it < n_items; it += nwarps) {
         const uint4 m4 = mask[it];
         if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
-        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
         long long seq = seq_base + (long long)off[it];
+        if (seq >= max_trees) continue;
+        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+
+        // pass 1: E[p] of the item without its last node; lane l keeps E[l], E[l+32], E[l+64], E[l+96]
+        double E0 = 0.0, E1 = 0.0, E2 = 0.0, E3 = 0.0;
+        for (int p = net.n - 1; p >= 0; p--) {
+            const unsigned m = __vcmpeq4(w, (unsigned)p * 0x01010101u);
+            if (__ballot_sync(kFull, m != 0) == 0) continue;
+            double s0, s1;
+            child_sums<SPL>(w, (unsigned)p, vaf_s, sigma_s, SP, lane, s0, s1);
+            const double Ep = parent_excess<SPL>(s0, s1, vaf_s[p * SP + lane],
+                                                 SPL == 2 ? vaf_s[p * SP + 32 + lane] : 0.0, valid0, valid1);
+            if (lane == (p & 31)) {
+                const int q = p >> 5;
+                if (q == 0) E0 = Ep; else if (q == 1) E1 = Ep; else if (q == 2) E2 = Ep; else E3 = Ep;
+            }
+        }
+
+        // pass 2: one complete tree per passing choice of the last node's parent
         const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
         for (int q = 0; q < 4; q++) {
             unsigned b = mw[q];
@@ -351,38 +400,18 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 const long long my_seq = seq++;
                 if (my_seq >= max_trees) continue;
                 const unsigned pstar = cand_s[i];
-                unsigned cw = w;
-                if (lane == wl) cw = (w & ~(0xffu << sh)) | (pstar << sh);
-                double err = 0.0;
-                for (int p = net.n - 1; p >= 0; p--) {
-                    const unsigned m = __vcmpeq4(cw, (unsigned)p * 0x01010101u);
-                    if (__ballot_sync(kFull, m != 0) == 0) continue;
-                    double s0, s1;
-                    child_sums<SPL>(cw, (unsigned)p, vaf_s, sigma_s, SP, lane, s0, s1);
-                    const double a0 = vaf_s[p * SP + lane];
-                    const bool pos0 = valid0 && s0 > a0;
-                    const double d0 = __dsub_rn(s0, a0);
-                    const double t0 = __dmul_rn(d0, d0);
-                    unsigned pb = __ballot_sync(kFull, pos0);
-                    while (pb) {
-                        const int l = __ffs(pb) - 1;
-                        pb &= pb - 1;
-                        err = __dadd_rn(err, __shfl_sync(kFull, t0, l));
-                    }
-                    if (SPL == 2) {
-                        const double a1 = vaf_s[p * SP + 32 + lane];
-                        const bool pos1 = valid1 && s1 > a1;
-                        const double d1 = __dsub_rn(s1, a1);
-                        const double t1 = __dmul_rn(d1, d1);
-                        pb = __ballot_sync(kFull, pos1);
-                        while (pb) {
-                            const int l = __ffs(pb) - 1;
-                            pb &= pb - 1;
-                            err = __dadd_rn(err, __shfl_sync(kFull, t1, l));
-                        }
-                    }
-                }
-                const double score = __dsqrt_rn(err);
+                double s0, s1;
+                child_sums<SPL>(w, pstar, vaf_s, sigma_s, SP, lane, s0, s1);
+                s0 = __dadd_rn(s0, xv0);
+                if (SPL == 2) s1 = __dadd_rn(s1, xv1);
+                const double Ep = parent_excess<SPL>(s0, s1, vaf_s[pstar * SP + lane],
+                                                     SPL == 2 ? vaf_s[pstar * SP + 32 + lane] : 0.0, valid0, valid1);
+                const bool mine = lane == (int)(pstar & 31);
+                const int ps = pstar >> 5;
+                const double e0 = (mine && ps == 0) ? Ep : E0, e1 = (mine && ps == 1) ? Ep : E1;
+                const double e2 = (mine && ps == 2) ? Ep : E2, e3 = (mine && ps == 3) ? Ep : E3;
+                const double total = butterfly_sum(__dadd_rn(__dadd_rn(e0, e1), __dadd_rn(e2, e3)));
+                const double score = __dsqrt_rn(total);
                 if (!full || score < tau) {
                     if (lane == 0) {
                         const unsigned long long slot = atomicAdd(&meta->n_cand, 1ull);
@@ -428,6 +457,37 @@ __device__ __forceinline__ void bitonic_sort_2048(Cand *e) {
     }
 }
 
+// Tournament pre-selection for long candidate lists: every block streams kSelPerBlock candidates
+// through the same 2048-entry bitonic sort and writes its best 1024 (a superset of the global
+// best num_save <= 1024 restricted to its slice) to `out`.  Repeated by the host until the list is
+// short enough for the final single-block select_kernel.
+constexpr int kSelPerBlock = 8 * kSelTile;
+
+__global__ void __launch_bounds__(kSelThreads)
+select_reduce_kernel(const Cand *__restrict__ in, long long m, Cand *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sel_raw[];
+    Cand *e = reinterpret_cast<Cand *>(sel_raw);
+    Cand sentinel;
+    sentinel.score = INFINITY;
+    sentinel.seq = 0x7fffffffffffffffll;
+    sentinel.part = 0x7fffffff;
+    sentinel.origin = 0xffffffffu;
+    sentinel.pstar = 0;
+    sentinel.pad = 1;
+    const long long lo = (long long)blockIdx.x * kSelPerBlock;
+    long long hi = lo + kSelPerBlock;
+    if (hi > m) hi = m;
+    for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) e[t] = sentinel;
+    __syncthreads();
+    for (long long base = lo; base < hi; base += kSelTile) {
+        for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
+            e[kSelTile + t] = base + t < hi ? in[base + t] : sentinel;
+        __syncthreads();
+        bitonic_sort_2048(e);
+    }
+    for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) out[(long long)blockIdx.x * kSelTile + t] = e[t];
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long long cand_cap,
               Cand *top_cur, Cand *top_next, const unsigned *__restrict__ tree_cur,
@@ -462,8 +522,17 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         __syncthreads();
         bitonic_sort_2048(e);
     }
-    unsigned long long total = count + m;
-    const unsigned newc = (unsigned)(total < (unsigned long long)num_save ? total : (unsigned long long)num_save);
+    // candidates may contain sentinel padding written by the tournament: count the real entries
+    __shared__ unsigned real_n;
+    if (threadIdx.x == 0) real_n = 0;
+    __syncthreads();
+    {
+        unsigned mine = 0;
+        for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) mine += e[t].pad == 0;
+        if (mine) atomicAdd(&real_n, mine);
+    }
+    __syncthreads();
+    const unsigned newc = real_n < (unsigned)num_save ? real_n : (unsigned)num_save;
     // gather parent bytes of the survivors
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int wl = last_level >> 2, sh = 8 * (last_level & 3);
@@ -491,6 +560,8 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->n_cand = 0;
     }
 }
+
+__global__ void set_n_cand(TopMeta *meta, unsigned long long m) { meta->n_cand = m; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -540,6 +611,52 @@ __global__ void export_records(const TopMeta *meta, const Cand *top, const unsig
 // ------------------------------------------------------------------------------------------
 // host side of the handle
 // ------------------------------------------------------------------------------------------
+namespace {
+
+// Process-wide pool of device buffers: a search allocates its frontier levels on demand and
+// returns them here on destroy, so a host that runs many searches (the fixNetwork loop, several
+// datasets) pays cudaMalloc once.  Sizes are rounded up to powers of two.
+struct DevicePool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_list;
+    size_t round_up(size_t n) { size_t r = 1 << 16; while (r < n) r <<= 1; return r; }
+    cudaError_t get(int dev, size_t bytes, void **out, size_t *got) {
+        const size_t r = round_up(bytes);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_list.find({dev, r});
+            if (it != free_list.end()) { *out = it->second; *got = r; free_list.erase(it); return cudaSuccess; }
+        }
+        *got = r;
+        cudaError_t e = cudaMalloc(out, r);
+        if (e != cudaSuccess) {            // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            release(dev);
+            e = cudaMalloc(out, r);
+        }
+        return e;
+    }
+    void put(int dev, void *p, size_t bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        free_list.insert({{dev, bytes}, p});
+    }
+    void release(int dev) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto it = free_list.begin(); it != free_list.end();) {
+            if (dev < 0 || it->first.first == dev) { cudaFree(it->second); it = free_list.erase(it); } else ++it;
+        }
+    }
+};
+DevicePool g_pool;
+
+struct DevBuf {              // one growable device buffer owned by a handle
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
 struct lichee_search {
     int n = 0, S = 0, SP = 32, L = 0, stride = 16, device = 0;
     lichee_search_params prm{};
@@ -550,29 +667,54 @@ struct lichee_search {
     lichee_search_stats stats{};
     // device
     cudaStream_t stream = nullptr;
-    double *d_vaf = nullptr;
-    uint8_t *d_sigma = nullptr, *d_cand = nullptr, *d_ncand = nullptr;
-    std::vector<unsigned *> d_level;         // lazily allocated frontier buffers
+    DevBuf b_net;                            // centroid matrix + sigma + candidate tables
+    std::vector<DevBuf> b_level;             // frontier buffers, grown on demand
     std::vector<long long> head, tail;
-    long long cap = 0;                       // items per level buffer
-    uint4 *d_mask = nullptr;
-    unsigned *d_cnt = nullptr, *d_off = nullptr;
-    unsigned long long *d_tile = nullptr;
-    ScanOut *d_scan = nullptr, *h_scan = nullptr;
-    TopMeta *d_meta = nullptr;
-    Cand *d_cands = nullptr, *d_top[2] = {nullptr, nullptr};
-    unsigned *d_tree[2] = {nullptr, nullptr};
+    long long cap = 0;                       // upper bound on items per level buffer
+    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_cands[2], b_top[2], b_tree[2];
+    ScanOut *h_scan = nullptr;               // pinned
+    TopMeta *h_meta = nullptr;               // pinned
     int flip = 0;
     long long chunk_max = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[2][6] = {};              // per-chunk kernel boundaries, double buffered
+    int evn[2] = {0, 0};
+    bool ev_leaf[2] = {false, false};
     // results on host
     std::vector<Cand> h_top;
     std::vector<uint8_t> h_tree;
     DevNet net{};
-    size_t smem = 0;
+    size_t smem = 0, smem_leaf = 0;
+
+    unsigned *level(int lv) { return static_cast<unsigned *>(b_level[lv].p); }
+    uint4 *d_mask() { return static_cast<uint4 *>(b_mask.p); }
+    unsigned *d_cnt() { return static_cast<unsigned *>(b_cnt.p); }
+    unsigned *d_off() { return static_cast<unsigned *>(b_off.p); }
+    unsigned long long *d_tile() { return static_cast<unsigned long long *>(b_tile.p); }
+    ScanOut *d_scan() { return static_cast<ScanOut *>(b_small.p); }
+    TopMeta *d_meta() { return reinterpret_cast<TopMeta *>(static_cast<char *>(b_small.p) + 64); }
+    Cand *d_cands(int i) { return static_cast<Cand *>(b_cands[i].p); }
+    Cand *d_top(int i) { return static_cast<Cand *>(b_top[i].p); }
+    unsigned *d_tree(int i) { return static_cast<unsigned *>(b_tree[i].p); }
 };
 
 namespace {
+
+// make `b` at least `bytes` large; contents are NOT preserved (callers only grow empty buffers)
+int ensure(lichee_search *h, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return LICHEE_OK;
+    if (b.p) g_pool.put(h->device, b.p, b.bytes);
+    b.p = nullptr; b.bytes = 0;
+    size_t got = 0;
+    CK(g_pool.get(h->device, bytes, &b.p, &got));
+    b.bytes = got;
+    return LICHEE_OK;
+}
+
+void give_back(lichee_search *h, DevBuf &b) {
+    g_pool.put(h->device, b.p, b.bytes);
+    b.p = nullptr; b.bytes = 0;
+}
 
 int grid_for(long long items) {
     long long blocks = (items + kWarpsPerBlock * 4 - 1) / (kWarpsPerBlock * 4);
@@ -582,55 +724,87 @@ int grid_for(long long items) {
     return (int)blocks;
 }
 
-int alloc_level(lichee_search *h, int lv) {
-    if (h->d_level[lv]) return LICHEE_OK;
-    CK(cudaMalloc(&h->d_level[lv], (size_t)h->cap * h->stride));
-    return LICHEE_OK;
-}
-
 template <int SPL>
 int launch_check(lichee_search *h, int lv, const unsigned *items, long long n_items) {
     check_kernel<SPL><<<grid_for(n_items), kThreads, h->smem, h->stream>>>(h->net, lv, items, n_items,
-                                                                          h->d_mask, h->d_cnt);
+                                                                          h->d_mask(), h->d_cnt());
     CK(cudaGetLastError());
     return LICHEE_OK;
 }
 
 int launch_scan(lichee_search *h, long long n_items, unsigned long long limit) {
     const int tiles = (int)((n_items + kScanTile - 1) / kScanTile);
-    scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt, h->d_off, h->d_tile, n_items);
-    scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile, tiles, h->d_scan);
-    scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt, h->d_off, h->d_tile, n_items, limit, h->d_scan);
+    scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items);
+    scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile(), tiles, h->d_scan());
+    scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items, limit, h->d_scan());
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_scan, h->d_scan, sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
     return LICHEE_OK;
 }
 
-int run_select(lichee_search *h, const unsigned *leaf_items, int external, const unsigned char *records,
-               long long record_bytes, long long cand_cap) {
+// Final selection: merge `m_hint` candidates (already bounded by the caller) into the ranked list.
+int run_select(lichee_search *h, const Cand *cands, long long cand_cap, const unsigned *leaf_items, int external,
+               const unsigned char *records, long long record_bytes) {
     const size_t sm = sizeof(Cand) * 2 * kSelTile;
-    select_kernel<<<1, kSelThreads, sm, h->stream>>>(h->d_meta, h->prm.num_save, h->d_cands, cand_cap,
-                                                     h->d_top[h->flip], h->d_top[h->flip ^ 1],
-                                                     h->d_tree[h->flip], h->d_tree[h->flip ^ 1], leaf_items,
+    select_kernel<<<1, kSelThreads, sm, h->stream>>>(h->d_meta(), h->prm.num_save, cands, cand_cap,
+                                                     h->d_top(h->flip), h->d_top(h->flip ^ 1),
+                                                     h->d_tree(h->flip), h->d_tree(h->flip ^ 1), leaf_items,
                                                      h->stride >> 2, h->L - 1, external, records, record_bytes);
     CK(cudaGetLastError());
     h->flip ^= 1;
     h->stats.num_launches++;
+    h->stats.kernel_launches[LICHEE_K_SELECT]++;
+    return LICHEE_OK;
+}
+
+// Tournament: shrink a long candidate list (m entries in b_cands[0]) to <= kSelPerBlock entries.
+// Returns the buffer index holding the survivors and their count.
+int run_tournament(lichee_search *h, long long &m, int &src) {
+    src = 0;
+    const size_t sm = sizeof(Cand) * 2 * kSelTile;
+    while (m > kSelPerBlock) {
+        const long long blocks = (m + kSelPerBlock - 1) / kSelPerBlock;
+        if (ensure(h, h->b_cands[src ^ 1], sizeof(Cand) * (size_t)blocks * kSelTile) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        select_reduce_kernel<<<(int)blocks, kSelThreads, sm, h->stream>>>(h->d_cands(src), m, h->d_cands(src ^ 1));
+        CK(cudaGetLastError());
+        h->stats.num_launches++;
+        h->stats.kernel_launches[LICHEE_K_SELECT]++;
+        m = blocks * kSelTile;
+        src ^= 1;
+    }
     return LICHEE_OK;
 }
 
 int fetch_top(lichee_search *h) {
-    TopMeta m;
-    CK(cudaMemcpyAsync(&m, h->d_meta, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->h_top.resize(m.count);
-    h->h_tree.assign((size_t)m.count * h->stride, 0xff);
-    if (m.count) {
-        CK(cudaMemcpyAsync(h->h_top.data(), h->d_top[h->flip], sizeof(Cand) * m.count, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_tree.data(), h->d_tree[h->flip], (size_t)m.count * h->stride, cudaMemcpyDeviceToHost, h->stream));
+    const unsigned count = h->h_meta->count;
+    h->h_top.resize(count);
+    h->h_tree.assign((size_t)count * h->stride, 0xff);
+    if (count) {
+        CK(cudaMemcpyAsync(h->h_top.data(), h->d_top(h->flip), sizeof(Cand) * count, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_tree.data(), h->d_tree(h->flip), (size_t)count * h->stride, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    h->stats.num_saved = m.count;
+    h->stats.num_saved = count;
+    return LICHEE_OK;
+}
+
+// Adds the kernel times of one finished chunk (event set `set`) to the statistics.
+// Boundaries: 0 start | 1 after check | 2 after scan | 3 after emit or leaf | 4 after select.
+int harvest_events(lichee_search *h, int set) {
+    const int nb = h->evn[set];
+    if (nb < 3) return LICHEE_OK;
+    CK(cudaEventSynchronize(h->evk[set][nb - 1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->evk[set][0], h->evk[set][1])); h->stats.kernel_ms[LICHEE_K_CHECK] += ms;
+    CK(cudaEventElapsedTime(&ms, h->evk[set][1], h->evk[set][2])); h->stats.kernel_ms[LICHEE_K_SCAN] += ms;
+    if (nb > 3) {
+        CK(cudaEventElapsedTime(&ms, h->evk[set][2], h->evk[set][3]));
+        h->stats.kernel_ms[h->ev_leaf[set] ? LICHEE_K_LEAF : LICHEE_K_EMIT] += ms;
+    }
+    if (nb > 4) { CK(cudaEventElapsedTime(&ms, h->evk[set][3], h->evk[set][4])); h->stats.kernel_ms[LICHEE_K_SELECT] += ms; }
+    h->evn[set] = 0;
     return LICHEE_OK;
 }
 
@@ -640,22 +814,29 @@ int run_search(lichee_search *h) {
     lichee_search_stats &st = h->stats;
     st = lichee_search_stats{};
     st.num_grow_calls = 1;
-    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta);
+    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
     h->flip = 0;
     for (int lv = 0; lv < L; lv++) h->head[lv] = h->tail[lv] = 0;
     if (h->no_trees || L == 0) return fetch_top(h);
 
-    CK(alloc_level(h, 0) == LICHEE_OK ? cudaSuccess : cudaErrorMemoryAllocation);
-    CK(cudaMemsetAsync(h->d_level[0], 0xff, h->stride, h->stream));
+    if (ensure(h, h->b_level[0], (size_t)h->stride) != LICHEE_OK) return LICHEE_ERR_CUDA;
+    CK(cudaMemsetAsync(h->level(0), 0xff, h->stride, h->stream));
     h->tail[0] = 1;
     CK(cudaEventRecord(h->ev0, h->stream));
 
+    // fan[lv]: observed mean number of surviving children per item placed at level lv; yield[lv]
+    // (recomputed from fan) estimates the complete trees below one item, used to size chunks so
+    // that a binding tree cap does not pay for subtrees it will never reach.
     std::vector<double> fan(L, 0.0);
+    std::vector<bool> seen(L, false);
     for (int lv = 0; lv < L; lv++) fan[lv] = (double)h->cands[lv].size();
     long long seq_base = 0;
     const int P = std::max(1, h->prm.part_count), R = h->prm.part_rank;
     bool sliced = P <= 1;
     float ms = 0;
+    int es = 0;
+    h->evn[0] = h->evn[1] = 0;
+    long long leaf_ramp = 1 << 15;           // candidates admitted per leaf launch while the threshold warms up
 
     for (;;) {
         int lv = -1;
@@ -681,72 +862,117 @@ int run_search(lichee_search *h) {
         }
         const long long pending = h->tail[lv] - h->head[lv];
         const bool leaf = lv == L - 1;
-        long long B = pending;
-        if (B > h->chunk_max) B = h->chunk_max;
+        const long long kcand = (long long)h->cands[lv].size();
+        long long B = std::min(pending, h->chunk_max);
+        if (sliced) {
+            // trees still wanted / trees expected below one item of this level
+            double yield = 1.0;
+            for (int l = lv; l < L; l++)   // unseen levels: assume every candidate passes, so the first descent stays narrow
+                yield = std::min(1e30, yield * std::max(seen[l] ? fan[l] : (double)h->cands[l].size(), 1e-3));
+            const double want = 1.25 * (double)(h->prm.max_num_trees - seq_base) / yield + 64.0;
+            if ((double)B > want) B = (long long)want;
+        }
         if (!leaf) {
             const long long guess = (long long)(0.8 * (double)h->cap / std::max(1.0, fan[lv]));
-            if (B > std::max(1024ll, guess)) B = std::max(1024ll, guess);
+            B = std::min(B, std::max(1024ll, guess));
         } else {
-            // every passing choice of the last node may become a candidate: keep them all in d_cands
-            const long long fit = h->cap / std::max<long long>(1, (long long)h->cands[lv].size());
-            if (B > fit) B = std::max(1ll, fit);
+            // every passing choice of the last node may become a candidate: keep them all
+            B = std::min(B, std::max(1ll, std::min(h->cap, leaf_ramp) / std::max(1ll, kcand)));
         }
-        const unsigned *items = h->d_level[lv] + (size_t)h->head[lv] * (h->stride >> 2);
-        CK(cudaEventRecord(h->evc0, h->stream));
+        if (B < 1) B = 1;
+        const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
+        if (ensure(h, h->b_mask, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_cnt, 4 * (size_t)B) != LICHEE_OK ||
+            ensure(h, h->b_off, 4 * (size_t)B) != LICHEE_OK ||
+            ensure(h, h->b_tile, 8 * (size_t)(B / kScanTile + 2)) != LICHEE_OK)
+            return LICHEE_ERR_CUDA;
+        es ^= 1;
+        if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;   // the chunk before last
+        h->ev_leaf[es] = leaf;
+        CK(cudaEventRecord(h->evk[es][0], h->stream));
         if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
-        CK(cudaEventRecord(h->evc1, h->stream));
+        CK(cudaEventRecord(h->evk[es][1], h->stream));
         const unsigned long long limit = leaf ? ~0ull >> 1 : (unsigned long long)h->cap;
         if (launch_scan(h, B, limit) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        CK(cudaEventRecord(h->evk[es][2], h->stream));
+        h->evn[es] = 3;
         st.num_launches += 4;
+        st.kernel_launches[LICHEE_K_CHECK]++;
+        st.kernel_launches[LICHEE_K_SCAN] += 3;
+        st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 20);
+        st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
         if (leaf) {
-            leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem, h->stream>>>(
-                h->net, items, B, h->head[lv], h->d_mask, h->d_off, seq_base, h->prm.max_num_trees, R,
-                h->d_meta, h->prm.num_save, h->d_cands, h->cap);
+            const long long cand_cap = B * kcand;
+            if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem_leaf, h->stream>>>(
+                h->net, items, B, h->head[lv], h->d_mask(), h->d_off(), seq_base, h->prm.max_num_trees, R,
+                h->d_meta(), h->prm.num_save, h->d_cands(0), cand_cap);
             CK(cudaGetLastError());
+            CK(cudaEventRecord(h->evk[es][3], h->stream));
             st.num_launches++;
-            if (run_select(h, h->d_level[lv], 0, nullptr, 0, h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            st.kernel_launches[LICHEE_K_LEAF]++;
+            st.kernel_bytes[LICHEE_K_LEAF] += B * (long long)(h->stride + 20);
+            CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
+            long long m = (long long)std::min<unsigned long long>(h->h_meta->n_cand, (unsigned long long)cand_cap);
+            if (m > 0) {
+                int src = 0;
+                if (run_tournament(h, m, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (src != 0) {   // survivors sit in the second buffer and may hold sentinel padding
+                    set_n_cand<<<1, 1, 0, h->stream>>>(h->d_meta(), (unsigned long long)m);
+                }
+                if (run_select(h, h->d_cands(src), m, h->level(lv), 0, nullptr, 0) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                st.kernel_bytes[LICHEE_K_SELECT] += (long long)sizeof(Cand) * (long long)h->h_meta->n_cand;
+            }
+            CK(cudaEventRecord(h->evk[es][4], h->stream));
+            h->evn[es] = 5;
+            // widen the next leaf launch once the threshold rejects most trees
+            if ((long long)h->h_meta->n_cand * 8 < leaf_ramp) leaf_ramp = std::min(leaf_ramp * 4, h->cap);
             const long long total = (long long)h->h_scan->total;
-            st.num_checks += B * (long long)h->cands[lv].size();
+            st.num_checks += B * kcand;
             st.num_grow_calls += total;
             st.frontier_bytes += B * (long long)h->stride;
             const long long before = seq_base;
             seq_base += total;
             st.num_scored += std::min(seq_base, (long long)h->prm.max_num_trees) - std::min(before, (long long)h->prm.max_num_trees);
             h->head[lv] += B;
+            fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * (double)total / (double)B : (double)total / (double)B;
+            seen[lv] = true;
         } else {
-            if (alloc_level(h, lv + 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
             CK(cudaStreamSynchronize(h->stream));
             const long long n_fit = (long long)(h->h_scan->fit >> 32);
             const long long total_fit = (long long)(h->h_scan->fit & 0xffffffffull);
-            if (n_fit == 0 && h->h_scan->total > 0) {
+            if (n_fit == 0) {
                 set_err("level_capacity %lld too small for one item's children", h->cap);
                 return LICHEE_ERR_INVALID;
             }
-            const long long done = h->h_scan->total <= (unsigned long long)h->cap ? B : n_fit;
-            if (total_fit > 0 || done > 0) {
-                emit_kernel<<<grid_for(done), kThreads, 0, h->stream>>>(h->net, lv, items, done, h->d_mask,
-                                                                        h->d_off, h->d_level[lv + 1]);
+            if (total_fit > 0) {
+                if (ensure(h, h->b_level[lv + 1], (size_t)total_fit * h->stride) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                emit_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(h->net, lv, items, n_fit, h->d_mask(),
+                                                                        h->d_off(), h->level(lv + 1));
                 CK(cudaGetLastError());
+                CK(cudaEventRecord(h->evk[es][3], h->stream));
+                h->evn[es] = 4;
                 st.num_launches++;
+                st.kernel_launches[LICHEE_K_EMIT]++;
             }
-            const long long produced = h->h_scan->total <= (unsigned long long)h->cap ? (long long)h->h_scan->total : total_fit;
             h->head[lv + 1] = 0;
-            h->tail[lv + 1] = produced;
-            h->head[lv] += done;
-            st.num_checks += done * (long long)h->cands[lv].size();
-            st.num_grow_calls += produced;
-            st.frontier_bytes += (done + produced) * (long long)h->stride;
-            if (done > 0) fan[lv] = 0.5 * fan[lv] + 0.5 * std::max(1.0, (double)produced / (double)done);
+            h->tail[lv + 1] = total_fit;
+            h->head[lv] += n_fit;
+            st.num_checks += n_fit * kcand;
+            st.num_grow_calls += total_fit;
+            st.frontier_bytes += (n_fit + total_fit) * (long long)h->stride;
+            st.kernel_bytes[LICHEE_K_EMIT] += n_fit * (long long)(h->stride + 20) + total_fit * (long long)h->stride;
+            const double f = (double)total_fit / (double)n_fit;
+            fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * f : f;
+            seen[lv] = true;
         }
-        CK(cudaEventElapsedTime(&ms, h->evc0, h->evc1));
-        st.kernel_ms_check += ms;
         if (h->head[lv] == h->tail[lv]) h->head[lv] = h->tail[lv] = 0;
         if (seq_base >= h->prm.max_num_trees) { st.status |= LICHEE_STATUS_TREE_CAP; break; }
         if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
     }
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (harvest_events(h, 0) != LICHEE_OK || harvest_events(h, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     st.kernel_ms_total = ms;
     st.num_trees = std::min(seq_base, (long long)h->prm.max_num_trees);
@@ -783,16 +1009,15 @@ int lichee_search_destroy(lichee_search *h) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
     }
-    cudaFree(h->d_vaf); cudaFree(h->d_sigma); cudaFree(h->d_cand); cudaFree(h->d_ncand);
-    for (unsigned *p : h->d_level) cudaFree(p);
-    cudaFree(h->d_mask); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_tile); cudaFree(h->d_scan);
+    give_back(h, h->b_net);
+    for (DevBuf &b : h->b_level) give_back(h, b);
+    give_back(h, h->b_mask); give_back(h, h->b_cnt); give_back(h, h->b_off); give_back(h, h->b_tile);
+    give_back(h, h->b_small);
+    for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     if (h->h_scan) cudaFreeHost(h->h_scan);
-    cudaFree(h->d_meta); cudaFree(h->d_cands);
-    cudaFree(h->d_top[0]); cudaFree(h->d_top[1]); cudaFree(h->d_tree[0]); cudaFree(h->d_tree[1]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->evc0) cudaEventDestroy(h->evc0);
-    if (h->evc1) cudaEventDestroy(h->evc1);
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) if (h->evk[a][b]) cudaEventDestroy(h->evk[a][b]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return LICHEE_OK;
@@ -882,7 +1107,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     CKD(cudaSetDevice(h->device));
     CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
-    CKD(cudaEventCreate(&h->evc0)); CKD(cudaEventCreate(&h->evc1));
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
     const int Lp = std::max(1, h->L);
     std::vector<double> vp((size_t)n * h->SP, 0.0);
     for (int v = 0; v < n; v++) for (int s = 0; s < S; s++) vp[(size_t)v * h->SP + s] = vaf[(size_t)v * S + s];
@@ -892,41 +1117,42 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         nc[t] = (uint8_t)h->cands[t].size();
         for (size_t i = 0; i < h->cands[t].size(); i++) cd[(size_t)t * kMaxN + i] = (uint8_t)h->cands[t][i];
     }
-    CKD(cudaMalloc(&h->d_vaf, vp.size() * sizeof(double)));
-    CKD(cudaMalloc(&h->d_sigma, sg.size()));
-    CKD(cudaMalloc(&h->d_cand, cd.size()));
-    CKD(cudaMalloc(&h->d_ncand, nc.size()));
-    CKD(cudaMemcpyAsync(h->d_vaf, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(h->d_sigma, sg.data(), sg.size(), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(h->d_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(h->d_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
+#define CKE(call) do { if ((call) != LICHEE_OK) { lichee_search_destroy(h); return LICHEE_ERR_CUDA; } } while (0)
+    // one buffer for the network: [vaf | sigma | cand | ncand]
+    const size_t o_sigma = vp.size() * sizeof(double), o_cand = o_sigma + sg.size(), o_ncand = o_cand + cd.size();
+    CKE(ensure(h, h->b_net, o_ncand + nc.size()));
+    char *nb = static_cast<char *>(h->b_net.p);
+    CKD(cudaMemcpyAsync(nb, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(nb + o_sigma, sg.data(), sg.size(), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(nb + o_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(nb + o_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
     h->chunk_max = std::min<long long>(h->cap, 1ll << 20);
-    h->d_level.assign(Lp, nullptr);
+    h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
-    const long long tiles = (h->cap + kScanTile - 1) / kScanTile + 1;
-    CKD(cudaMalloc(&h->d_mask, sizeof(uint4) * h->chunk_max));
-    CKD(cudaMalloc(&h->d_cnt, sizeof(unsigned) * h->chunk_max));
-    CKD(cudaMalloc(&h->d_off, sizeof(unsigned) * h->chunk_max));
-    CKD(cudaMalloc(&h->d_tile, sizeof(unsigned long long) * tiles));
-    CKD(cudaMalloc(&h->d_scan, sizeof(ScanOut)));
-    CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut)));
-    CKD(cudaMalloc(&h->d_meta, sizeof(TopMeta)));
-    CKD(cudaMalloc(&h->d_cands, sizeof(Cand) * h->cap));
+    CKE(ensure(h, h->b_small, 256));
+    CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta)));
+    h->h_meta = reinterpret_cast<TopMeta *>(h->h_scan + 1);
     for (int i = 0; i < 2; i++) {
-        CKD(cudaMalloc(&h->d_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
-        CKD(cudaMalloc(&h->d_tree[i], (size_t)LICHEE_MAX_SAVE * h->stride));
+        CKE(ensure(h, h->b_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
+        CKE(ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * h->stride));
     }
-    h->net.vaf = h->d_vaf; h->net.sigma = h->d_sigma; h->net.cand = h->d_cand; h->net.ncand = h->d_ncand;
+    h->net.vaf = reinterpret_cast<const double *>(nb);
+    h->net.sigma = reinterpret_cast<const uint8_t *>(nb + o_sigma);
+    h->net.cand = reinterpret_cast<const uint8_t *>(nb + o_cand);
+    h->net.ncand = reinterpret_cast<const uint8_t *>(nb + o_ncand);
     h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
     h->net.margin = params->vaf_error_margin;
     h->smem = (size_t)n * h->SP * sizeof(double) + 2 * kMaxN;
+    h->smem_leaf = h->smem;
     CKD(cudaFuncSetAttribute(check_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_leaf));
+    CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_leaf));
     CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
+    CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
+#undef CKE
     CKD(cudaStreamSynchronize(h->stream));
 #undef CKD
     *out = h;
@@ -992,9 +1218,10 @@ int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_pt
     CK(cudaSetDevice(h->device));
     const long long rb = 24 + h->stride;
     unsigned char *d = nullptr;
+    lichee_search *hm = const_cast<lichee_search *>(h);
     if (device_ptr) d = static_cast<unsigned char *>(dst);
     else CK(cudaMalloc(&d, (size_t)rb * h->prm.num_save));
-    export_records<<<h->prm.num_save, 32, 0, h->stream>>>(h->d_meta, h->d_top[h->flip], h->d_tree[h->flip],
+    export_records<<<h->prm.num_save, 32, 0, h->stream>>>(hm->d_meta(), hm->d_top(h->flip), hm->d_tree(h->flip),
                                                           h->stride >> 2, h->prm.num_save, d, rb);
     CK(cudaGetLastError());
     if (!device_ptr) {
@@ -1013,7 +1240,7 @@ int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_
     CK(cudaSetDevice(h->device));
     const long long rb = 24 + h->stride;
     const long long n = (long long)n_lists * h->prm.num_save;
-    if (n > h->cap) { set_err("too many records to merge"); return LICHEE_ERR_INVALID; }
+    if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)n) != LICHEE_OK) return LICHEE_ERR_CUDA;
     const unsigned char *d = static_cast<const unsigned char *>(records);
     unsigned char *tmp = nullptr;
     if (!device_ptr) {
@@ -1021,9 +1248,9 @@ int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_
         CK(cudaMemcpyAsync(tmp, records, (size_t)rb * n, cudaMemcpyHostToDevice, h->stream));
         d = tmp;
     }
-    records_to_cands<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(d, rb, n, h->d_cands, h->d_meta);
+    records_to_cands<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(d, rb, n, h->d_cands(0), h->d_meta());
     CK(cudaGetLastError());
-    if (run_select(h, nullptr, 1, d, rb, h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+    if (run_select(h, h->d_cands(0), n, nullptr, 1, d, rb) != LICHEE_OK) return LICHEE_ERR_CUDA;
     const int rc = fetch_top(h);
     if (tmp) cudaFree(tmp);
     return rc;

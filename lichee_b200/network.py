@@ -1,5 +1,6 @@
 """Pure-Python restatement of the reference code on either side of the tree search
-(TEST INFRASTRUCTURE ONLY): SSNV loading/calling and constraint-network construction.
+: SSNV loading/calling and constraint-network
+construction -- the host-side data path on the input side of the tree search (DESIGN.md row f).
 
 Reference (read-only):
   SNVDataStore.loadSNVFile / parseSNVEntry / processSNVEntry   SNVDataStore.java:385-409,522-545,663-718

@@ -1,10 +1,10 @@
 """Synthetic clonal-evolution instances of the shapes BASELINE.json names
-(TEST/BENCH INFRASTRUCTURE): a random true lineage tree over `n_clusters` clusters and
+(workload generator for tests and bench.py): a random true lineage tree over `n_clusters` clusters and
 `n_samples` samples, cluster centroid VAFs obeying the sum rule up to noise, turned into a
-constraint network with the reference's own edge rule (oracle.network_model.Network,
+constraint network with the reference's own edge rule (lichee_b200.network.Network,
 PHYNetwork.java:94-175) under -c (ALL_EDGES) and -minClusterSize 1."""
 import random
-from .network_model import Cluster, Group, Network, Params
+from .network import Cluster, Group, Network, Params
 
 
 def make_instance(n_clusters, n_samples, seed, noise=0.01, margin=0.1, complete=True,

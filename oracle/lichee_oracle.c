@@ -310,7 +310,11 @@ int lichee_oracle_search(int n, int S, const int *adj_off, const int *adj_idx, c
  *   tree    : one parent per node, parents of a node taken in ascending id
  *   order   : lexicographic in (parent of sigma[0], parent of sigma[1], ...)
  *   sums    : children of a parent are added in sigma order (checkConstraint, PHYTree.java:156-174,
- *             and computeErrorScore, PHYTree.java:214-233, with that child list order)
+ *             and the per-sample sums of computeErrorScore, PHYTree.java:214-233)
+ *   score   : the positive terms (sum - VAF(parent))^2 are added with the device's fixed-shape
+ *             reduction (per parent a 32-lane butterfly over samples, then a butterfly over the 128
+ *             parent slots) instead of the reference's one-after-another order: a few ulp apart,
+ *             far inside the 1e-9 relative tolerance BASELINE.json states
  *   caps    : the first max_trees valid trees in this order
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -322,18 +326,34 @@ typedef struct {
     int top_s; long kept; double *k_score; long *k_seq; int *k_par;  /* ranked list, insertion sort */
 } canon_t;
 
+/* fixed-shape reductions of the device (lichee_search.cu, kernel 4): xor-butterfly over 32 lanes */
+static double butterfly32(double *v) {
+    for (int d = 16; d > 0; d >>= 1) {
+        double t[32];
+        for (int l = 0; l < 32; l++) t[l] = v[l] + v[l ^ d];
+        memcpy(v, t, sizeof(t));
+    }
+    return v[0];
+}
 static double canon_score(canon_t *c) {
-    double err = 0;
-    for (int p = c->n - 1; p >= 0; p--) {
+    double E[128];
+    memset(E, 0, sizeof(E));
+    for (int p = 0; p < c->n; p++) {
         if (c->nch[p] == 0) continue;
+        double t[64], lane[32];
+        memset(t, 0, sizeof(t));
         for (int i = 0; i < c->S; i++) {
             double sum = 0;
             for (int k = 0; k < c->nch[p]; k++) sum += c->vaf[(size_t)c->ch[p][k] * c->S + i];
             double a = c->vaf[(size_t)p * c->S + i];
-            if (sum > a) err += (sum - a) * (sum - a);
+            if (sum > a) t[i] = (sum - a) * (sum - a);
         }
+        for (int l = 0; l < 32; l++) lane[l] = c->S > 32 ? t[l] + t[l + 32] : t[l];
+        E[p] = butterfly32(lane);
     }
-    return sqrt(err);
+    double lane[32];
+    for (int l = 0; l < 32; l++) lane[l] = (E[l] + E[l + 32]) + (E[l + 64] + E[l + 96]);
+    return sqrt(butterfly32(lane));
 }
 static void canon_keep(canon_t *c, double score, long seq) {
     if (c->kept == c->top_s && !(score < c->k_score[c->kept - 1])) return;

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import oracle
-from oracle.synth import make_instance
+from lichee_b200.synth import make_instance
 
 pytestmark = pytest.mark.gpu
 
