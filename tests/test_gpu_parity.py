@@ -180,3 +180,47 @@ def test_sharded_search_merges_to_the_single_gpu_answer(built):
         assert [t.errorScore for t in merged] == [t.errorScore for t in trees]
         for p in parts:
             p.close()
+
+
+def _networks():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "networks_bundled.json")))
+
+
+def test_bundled_datasets_match_the_reference_search(built):
+    """BASELINE configs[0..2]: every bundled ccRCC / HGSC network (README settings, with and
+    without -c) through the CUDA path against what the literal reference search returned when the
+    fixture was generated: same number of valid trees, same ranked scores (1e-9), and the same
+    ranked trees wherever the reference's scores are distinct."""
+    for e in _networks():
+        g = e["reference_search"]
+        if g["n_trees"] >= 100000:          # the reference stopped at MAX_NUM_TREES: a DFS prefix, not comparable
+            continue
+        st, trees, _ = gpu_search(e["adj"], np.array(e["aaf"]), e["vaf_error_margin"], 100, max_num_trees=10**9)
+        assert st["num_trees"] == g["n_trees"], e["dataset"]
+        assert len(trees) == len(g["scores"])
+        for k, t in enumerate(trees):
+            assert abs(g["scores"][k] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
+        rs = g["scores"]
+        for k, t in enumerate(trees):
+            lo = k == 0 or rs[k] - rs[k - 1] > 1e-7 * max(rs[k], 1e-12)
+            hi = k + 1 >= len(rs) or rs[k + 1] - rs[k] > 1e-7 * max(rs[k], 1e-12)
+            if lo and hi and len(trees) == g["n_trees"]:
+                assert t.parent == g["parents"][k], (e["dataset"], k)
+
+
+def test_published_reference_trees_on_gpu(built):
+    """The top trees the reference publishes for ccRCC RK26 and RMH008 (img_demo/*.dot.png)."""
+    import json, os
+    pub = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "published_trees.json")))
+    nets = _networks()
+    for p in pub:
+        e = [x for x in nets if (x["dataset"], x["clustering"], x["complete_edges"]) ==
+             (p["dataset"], p["clustering"], p["complete_edges"])][0]
+        st, trees, _ = gpu_search(e["adj"], np.array(e["aaf"]), e["vaf_error_margin"], 1)
+        par = trees[0].parent
+        edges = sorted(["GL" if par[v] == 0 else e["tags"][par[v]], e["tags"][v]] for v in range(1, len(par)))
+        assert edges == sorted(p["edges"])
+        # treeNodes / treeEdges reconstruction is consistent
+        assert trees[0].treeNodes[0] == 0 and sorted(trees[0].treeNodes) == list(range(len(par)))
+        assert all(par[c] == q for q, ch in trees[0].treeEdges.items() for c in ch)
