@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--save", type=int, default=1000)
-    ap.add_argument("--max-trees", type=int, default=1 << 26)
+    ap.add_argument("--max-trees", type=int, default=1 << 30)
     ap.add_argument("--level-capacity", type=int, default=0)
     ap.add_argument("--ref-grow-calls", type=int, default=1500000)
     ap.add_argument("--cpu-baseline-grow-calls", type=int, default=5000000)
