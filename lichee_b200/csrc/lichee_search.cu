@@ -70,13 +70,19 @@ void set_err(const char *fmt, ...) {
 // device-side description of one network
 // ------------------------------------------------------------------------------------------
 struct DevNet {
-    const double *vaf;       // [n][SP]   centroid matrix, rows by node id, zero padded to SP
-    const uint8_t *sigma;    // [L]       node placed at tree level t (0-based position)
-    const uint8_t *cand;     // [L][128]  candidate parents of sigma[t], ascending node id
+    const double *vaf;       // [n][SP]   centroid matrix, row q: q = 0 germline root, q = t+1 node sigma[t]
+    const uint8_t *cand;     // [L][128]  candidate parents of sigma[t] as row indices q, in ascending NODE id
     const uint8_t *ncand;    // [L]
+    const uint4 *static_ok;  // [L]       bit i: candidate i passes the sum rule when it has no other child
     int n, S, SP, L, stride; // stride = bytes per frontier item (multiple of 16, <= 128)
     double margin;
 };
+
+// Frontier item layout: an item is W = stride/4 words; the parent (row index q) of tree position t
+// lives in byte t/W of word t%W, so lane l of the warp that loads the item holds positions l, l+W,
+// l+2W, l+3W in bytes 0..3 of its word and the children of a parent come out of <= 4 ballots in
+// position order.
+__host__ __device__ __forceinline__ int item_byte(int t, int W) { return 4 * (t % W) + t / W; }
 
 struct Cand {                // one scored complete tree that beat the current threshold
     double score;
@@ -105,43 +111,50 @@ __device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b) {
     return a.seq < b.seq;
 }
 
-// Shared-memory staging of the centroid matrix and the per-level tables.
-template <int SPL>
-__device__ __forceinline__ void stage_network(const DevNet &net, int level, double *vaf_s,
-                                              uint8_t *sigma_s, uint8_t *cand_s) {
+// Shared-memory staging of the centroid matrix and the candidate table of one level.
+__device__ __forceinline__ void stage_network(const DevNet &net, int level, double *vaf_s, uint8_t *cand_s) {
     const int words = net.n * net.SP;
     for (int i = threadIdx.x; i < words; i += blockDim.x) vaf_s[i] = net.vaf[i];
-    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) {
-        sigma_s[i] = i < net.L ? net.sigma[i] : 0;
-        cand_s[i] = net.cand[(size_t)level * kMaxN + i];
-    }
+    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) cand_s[i] = net.cand[(size_t)level * kMaxN + i];
     __syncthreads();
 }
 
-// Sum of the centroid rows of the children of candidate parent p inside item word-vector w
-// (lane l holds parent bytes 4l..4l+3), in ascending tree-level order: the canonical
-// accumulation order.  Returns the sums for samples lane and lane+32.
+// Sum of the centroid rows of the children of parent q inside item word-vector w, in ascending tree
+// position: the canonical accumulation order.  rmax = highest byte lane that can hold an
+// assigned position.  Returns the sums for samples lane and lane+32.
 template <int SPL>
-__device__ __forceinline__ void child_sums(unsigned w, unsigned p, const double *vaf_s,
-                                           const uint8_t *sigma_s, int SP, int lane, double &s0,
-                                           double &s1) {
-    const unsigned m = __vcmpeq4(w, p * 0x01010101u);
-    unsigned any = __ballot_sync(kFull, m != 0);
+__device__ __forceinline__ void child_sums(unsigned w, unsigned q, int rmax, int W, const double *vaf_s, int SP,
+                                           int lane, double &s0, double &s1) {
+    const unsigned m = __vcmpeq4(w, q * 0x01010101u);
     s0 = 0.0;
     s1 = 0.0;
-    while (any) {
-        const int l = __ffs(any) - 1;
-        any &= any - 1;
-        const unsigned mm = __shfl_sync(kFull, m, l);
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (mm & (0xffu << (8 * r))) {
-                const int c = sigma_s[l * 4 + r];
-                s0 = __dadd_rn(s0, vaf_s[c * SP + lane]);
-                if (SPL == 2) s1 = __dadd_rn(s1, vaf_s[c * SP + 32 + lane]);
-            }
+    for (int r = 0; r <= rmax; r++) {
+        unsigned kids = __ballot_sync(kFull, (m >> (8 * r)) & 1u);
+        while (kids) {
+            const int row = r * W + __ffs(kids);             // position + 1 = row of the child
+            kids &= kids - 1;
+            s0 = __dadd_rn(s0, vaf_s[row * SP + lane]);
+            if (SPL == 2) s1 = __dadd_rn(s1, vaf_s[row * SP + 32 + lane]);
         }
     }
+}
+
+// 128-bit set of the rows that are the parent of at least one assigned position of the item.
+__device__ __forceinline__ void parent_presence(unsigned w, int rmax, unsigned pm[4]) {
+    unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    for (int r = 0; r <= rmax; r++) {
+        const unsigned b = (w >> (8 * r)) & 0xffu;
+        const unsigned bit = b < 128u ? 1u << (b & 31) : 0u;
+        const unsigned k = b >> 5;
+        m0 |= k == 0 ? bit : 0u;
+        m1 |= k == 1 ? bit : 0u;
+        m2 |= k == 2 ? bit : 0u;
+        m3 |= k == 3 ? bit : 0u;
+    }
+    pm[0] = __reduce_or_sync(kFull, m0);
+    pm[1] = __reduce_or_sync(kFull, m1);
+    pm[2] = __reduce_or_sync(kFull, m2);
+    pm[3] = __reduce_or_sync(kFull, m3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -155,16 +168,17 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
              uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
-    uint8_t *sigma_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
-    uint8_t *cand_s = sigma_s + kMaxN;
-    stage_network<SPL>(net, level, vaf_s, sigma_s, cand_s);
+    uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    stage_network(net, level, vaf_s, cand_s);
 
     const int lane = threadIdx.x & 31;
     const int SP = net.SP;
     const int k = net.ncand[level];
-    const int v = sigma_s[level];
-    const double xv0 = vaf_s[v * SP + lane];
-    const double xv1 = SPL == 2 ? vaf_s[v * SP + 32 + lane] : 0.0;
+    const uint4 sok4 = net.static_ok[level];
+    const unsigned sok[4] = {sok4.x, sok4.y, sok4.z, sok4.w};
+    const int rmax = level > 0 ? (level - 1) / (net.stride >> 2) : -1;
+    const double xv0 = vaf_s[(level + 1) * SP + lane];
+    const double xv1 = SPL == 2 ? vaf_s[(level + 1) * SP + 32 + lane] : 0.0;
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const int wstride = net.stride >> 2;
@@ -173,27 +187,37 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
 
     for (long long it = warp0; it < n_items; it += nwarps) {
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
-        unsigned bits = 0, cnt = 0;
-        for (int i = 0; i < k; i++) {
-            const unsigned p = cand_s[i];
-            double s0, s1;
-            child_sums<SPL>(w, p, vaf_s, sigma_s, SP, lane, s0, s1);
-            s0 = __dadd_rn(s0, xv0);
-            bool bad = valid0 && s0 > __dadd_rn(vaf_s[p * SP + lane], net.margin);
-            if (SPL == 2) {
-                s1 = __dadd_rn(s1, xv1);
-                bad |= valid1 && s1 > __dadd_rn(vaf_s[p * SP + 32 + lane], net.margin);
+        unsigned pm[4];
+        parent_presence(w, rmax, pm);
+        unsigned bits[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {                       // static indices keep the masks in registers
+            unsigned bg = 0;
+            const int hi = k - g * 32 < 32 ? k - g * 32 : 32;
+            for (int j = 0; j < hi; j++) {
+                const unsigned q = cand_s[g * 32 + j];
+                const unsigned pw = (q >> 5) == 0 ? pm[0] : (q >> 5) == 1 ? pm[1] : (q >> 5) == 2 ? pm[2] : pm[3];
+                bool pass;
+                if ((pw >> (q & 31)) & 1u) {
+                    double s0, s1;
+                    child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
+                    s0 = __dadd_rn(s0, xv0);
+                    bool bad = valid0 && s0 > __dadd_rn(vaf_s[q * SP + lane], net.margin);
+                    if (SPL == 2) {
+                        s1 = __dadd_rn(s1, xv1);
+                        bad |= valid1 && s1 > __dadd_rn(vaf_s[q * SP + 32 + lane], net.margin);
+                    }
+                    pass = !__any_sync(kFull, bad);
+                } else {
+                    pass = (sok[g] >> j) & 1u;               // no other child: decided once per network
+                }
+                if (pass) bg |= 1u << j;
             }
-            if (!__any_sync(kFull, bad)) {
-                cnt++;
-                if (lane == (i >> 5)) bits |= 1u << (i & 31);
-            }
+            bits[g] = bg;
         }
-        const unsigned b0 = __shfl_sync(kFull, bits, 0), b1 = __shfl_sync(kFull, bits, 1);
-        const unsigned b2 = __shfl_sync(kFull, bits, 2), b3 = __shfl_sync(kFull, bits, 3);
         if (lane == 0) {
-            mask_out[it] = make_uint4(b0, b1, b2, b3);
-            count_out[it] = cnt;
+            mask_out[it] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+            count_out[it] = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
         }
     }
 }
@@ -284,7 +308,7 @@ emit_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int wstride = net.stride >> 2;
-    const int wl = level >> 2, sh = 8 * (level & 3);
+    const int wl = item_byte(level, wstride) >> 2, sh = 8 * (item_byte(level, wstride) & 3);
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     for (long long it = warp0; it < n_items; it += nwarps) {
@@ -294,10 +318,10 @@ emit_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long
         long long dst = (long long)off[it];
         const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            unsigned b = mw[q];
+        for (int g = 0; g < 4; g++) {
+            unsigned b = mw[g];
             while (b) {
-                const int i = q * 32 + __ffs(b) - 1;
+                const int i = g * 32 + __ffs(b) - 1;
                 b &= b - 1;
                 unsigned cw = w;
                 if (lane == wl) cw = (w & ~(0xffu << sh)) | ((unsigned)cand_s[i] << sh);
@@ -350,19 +374,18 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             long long cand_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
-    uint8_t *sigma_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
-    uint8_t *cand_s = sigma_s + kMaxN;
+    uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
     const int level = net.L - 1;
-    stage_network<SPL>(net, level, vaf_s, sigma_s, cand_s);
+    stage_network(net, level, vaf_s, cand_s);
 
     const int lane = threadIdx.x & 31;
     const int SP = net.SP;
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const int wstride = net.stride >> 2;
-    const int v = sigma_s[level];
-    const double xv0 = vaf_s[v * SP + lane];
-    const double xv1 = SPL == 2 ? vaf_s[v * SP + 32 + lane] : 0.0;
+    const int rmax = level > 0 ? (level - 1) / (net.stride >> 2) : -1;
+    const double xv0 = vaf_s[(level + 1) * SP + lane];
+    const double xv1 = SPL == 2 ? vaf_s[(level + 1) * SP + 32 + lane] : 0.0;
     const double tau = meta->tau;
     const bool full = meta->count >= (unsigned)num_save;
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -374,42 +397,58 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         long long seq = seq_base + (long long)off[it];
         if (seq >= max_trees) continue;
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+        const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
 
-        // pass 1: E[p] of the item without its last node; lane l keeps E[l], E[l+32], E[l+64], E[l+96]
-        double E0 = 0.0, E1 = 0.0, E2 = 0.0, E3 = 0.0;
-        for (int p = net.n - 1; p >= 0; p--) {
-            const unsigned m = __vcmpeq4(w, (unsigned)p * 0x01010101u);
-            if (__ballot_sync(kFull, m != 0) == 0) continue;
-            double s0, s1;
-            child_sums<SPL>(w, (unsigned)p, vaf_s, sigma_s, SP, lane, s0, s1);
-            const double Ep = parent_excess<SPL>(s0, s1, vaf_s[p * SP + lane],
-                                                 SPL == 2 ? vaf_s[p * SP + 32 + lane] : 0.0, valid0, valid1);
-            if (lane == (p & 31)) {
-                const int q = p >> 5;
-                if (q == 0) E0 = Ep; else if (q == 1) E1 = Ep; else if (q == 2) E2 = Ep; else E3 = Ep;
+        // rows that matter: parents present in the item, plus the passing choices for the last node
+        unsigned um[4], pq[4] = {0, 0, 0, 0};
+        parent_presence(w, rmax, um);
+        for (int g = 0; g < 4; g++) {
+            unsigned b = mw[g];
+            while (b) {
+                const unsigned q = cand_s[g * 32 + __ffs(b) - 1];
+                b &= b - 1;
+                pq[q >> 5] |= 1u << (q & 31);
+            }
+        }
+        // single pass: E[q] of the item without its last node and, for passing choices, E'[q] with
+        // the last node added.  Lane l keeps rows l, l+32, l+64, l+96 of both.
+        double E0 = 0.0, E1 = 0.0, E2 = 0.0, E3 = 0.0, F0 = 0.0, F1 = 0.0, F2 = 0.0, F3 = 0.0;
+        for (int g = 0; g < 4; g++) {
+            unsigned rows = um[g] | pq[g];
+            while (rows) {
+                const int bq = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const unsigned q = g * 32 + bq;
+                double s0, s1;
+                child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
+                const double a0 = vaf_s[q * SP + lane], a1 = SPL == 2 ? vaf_s[q * SP + 32 + lane] : 0.0;
+                const double Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                double Fq = 0.0;
+                if ((pq[g] >> bq) & 1u) {
+                    s0 = __dadd_rn(s0, xv0);
+                    if (SPL == 2) s1 = __dadd_rn(s1, xv1);
+                    Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                }
+                if (lane == bq) {
+                    if (g == 0) { E0 = Eq; F0 = Fq; } else if (g == 1) { E1 = Eq; F1 = Fq; }
+                    else if (g == 2) { E2 = Eq; F2 = Fq; } else { E3 = Eq; F3 = Fq; }
+                }
             }
         }
 
-        // pass 2: one complete tree per passing choice of the last node's parent
-        const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
-        for (int q = 0; q < 4; q++) {
-            unsigned b = mw[q];
+        // one complete tree per passing choice: swap one slot, reduce
+        for (int g = 0; g < 4; g++) {
+            unsigned b = mw[g];
             while (b) {
-                const int i = q * 32 + __ffs(b) - 1;
+                const int i = g * 32 + __ffs(b) - 1;
                 b &= b - 1;
                 const long long my_seq = seq++;
                 if (my_seq >= max_trees) continue;
-                const unsigned pstar = cand_s[i];
-                double s0, s1;
-                child_sums<SPL>(w, pstar, vaf_s, sigma_s, SP, lane, s0, s1);
-                s0 = __dadd_rn(s0, xv0);
-                if (SPL == 2) s1 = __dadd_rn(s1, xv1);
-                const double Ep = parent_excess<SPL>(s0, s1, vaf_s[pstar * SP + lane],
-                                                     SPL == 2 ? vaf_s[pstar * SP + 32 + lane] : 0.0, valid0, valid1);
-                const bool mine = lane == (int)(pstar & 31);
-                const int ps = pstar >> 5;
-                const double e0 = (mine && ps == 0) ? Ep : E0, e1 = (mine && ps == 1) ? Ep : E1;
-                const double e2 = (mine && ps == 2) ? Ep : E2, e3 = (mine && ps == 3) ? Ep : E3;
+                const unsigned q = cand_s[i];
+                const bool mine = lane == (int)(q & 31);
+                const int ps = q >> 5;
+                const double e0 = (mine && ps == 0) ? F0 : E0, e1 = (mine && ps == 1) ? F1 : E1;
+                const double e2 = (mine && ps == 2) ? F2 : E2, e3 = (mine && ps == 3) ? F3 : E3;
                 const double total = butterfly_sum(__dadd_rn(__dadd_rn(e0, e1), __dadd_rn(e2, e3)));
                 const double score = __dsqrt_rn(total);
                 if (!full || score < tau) {
@@ -421,7 +460,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                             c.seq = my_seq;
                             c.part = part;
                             c.origin = (unsigned)(item_base + it);
-                            c.pstar = pstar;
+                            c.pstar = q;
                             c.pad = 0;
                             cands[slot] = c;
                         }
@@ -535,7 +574,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
     const unsigned newc = real_n < (unsigned)num_save ? real_n : (unsigned)num_save;
     // gather parent bytes of the survivors
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int wl = last_level >> 2, sh = 8 * (last_level & 3);
+    const int wl = item_byte(last_level, wstride) >> 2, sh = 8 * (item_byte(last_level, wstride) & 3);
     for (unsigned t = wid; t < newc; t += kSelThreads / 32) {
         const Cand c = e[t];
         unsigned w = 0xffffffffu;
@@ -1109,21 +1148,37 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
     for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
     const int Lp = std::max(1, h->L);
+    // row index q of every node: 0 = root, t+1 = sigma[t]
+    std::vector<int> qof(n, 0);
+    for (int t = 0; t < h->L; t++) qof[h->sigma[t]] = t + 1;
     std::vector<double> vp((size_t)n * h->SP, 0.0);
-    for (int v = 0; v < n; v++) for (int s = 0; s < S; s++) vp[(size_t)v * h->SP + s] = vaf[(size_t)v * S + s];
-    std::vector<uint8_t> sg(kMaxN, 0), cd((size_t)Lp * kMaxN, 0), nc(kMaxN, 0);
+    for (int v = 0; v < n; v++) for (int s = 0; s < S; s++) vp[(size_t)qof[v] * h->SP + s] = vaf[(size_t)v * S + s];
+    std::vector<uint8_t> cd((size_t)Lp * kMaxN, 0), nc(kMaxN, 0);
+    std::vector<uint4> sok(Lp, make_uint4(0, 0, 0, 0));
     for (int t = 0; t < h->L; t++) {
-        sg[t] = (uint8_t)h->sigma[t];
         nc[t] = (uint8_t)h->cands[t].size();
-        for (size_t i = 0; i < h->cands[t].size(); i++) cd[(size_t)t * kMaxN + i] = (uint8_t)h->cands[t][i];
+        unsigned bits[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i < h->cands[t].size(); i++) {
+            const int p = h->cands[t][i], v = h->sigma[t];
+            cd[(size_t)t * kMaxN + i] = (uint8_t)qof[p];
+            // the sum rule for p with v as its only child: 0.0 + VAF(v) > VAF(p) + margin  (same doubles as the kernel)
+            bool ok = true;
+            for (int s = 0; s < S; s++) {
+                volatile double sum = 0.0 + vaf[(size_t)v * S + s];
+                volatile double capv = vaf[(size_t)p * S + s] + params->vaf_error_margin;
+                if (sum > capv) ok = false;
+            }
+            if (ok) bits[i >> 5] |= 1u << (i & 31);
+        }
+        sok[t] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
     }
 #define CKE(call) do { if ((call) != LICHEE_OK) { lichee_search_destroy(h); return LICHEE_ERR_CUDA; } } while (0)
-    // one buffer for the network: [vaf | sigma | cand | ncand]
-    const size_t o_sigma = vp.size() * sizeof(double), o_cand = o_sigma + sg.size(), o_ncand = o_cand + cd.size();
+    // one buffer for the network: [vaf | static_ok | cand | ncand]
+    const size_t o_sok = vp.size() * sizeof(double), o_cand = o_sok + sok.size() * sizeof(uint4), o_ncand = o_cand + cd.size();
     CKE(ensure(h, h->b_net, o_ncand + nc.size()));
     char *nb = static_cast<char *>(h->b_net.p);
     CKD(cudaMemcpyAsync(nb, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(nb + o_sigma, sg.data(), sg.size(), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(nb + o_sok, sok.data(), sok.size() * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
@@ -1139,12 +1194,12 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         CKE(ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * h->stride));
     }
     h->net.vaf = reinterpret_cast<const double *>(nb);
-    h->net.sigma = reinterpret_cast<const uint8_t *>(nb + o_sigma);
+    h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
     h->net.cand = reinterpret_cast<const uint8_t *>(nb + o_cand);
     h->net.ncand = reinterpret_cast<const uint8_t *>(nb + o_ncand);
     h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
     h->net.margin = params->vaf_error_margin;
-    h->smem = (size_t)n * h->SP * sizeof(double) + 2 * kMaxN;
+    h->smem = (size_t)n * h->SP * sizeof(double) + kMaxN;
     h->smem_leaf = h->smem;
     CKD(cudaFuncSetAttribute(check_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -1188,15 +1243,22 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
     if (score) *score = h->h_top[k].score;
     if (seq) *seq = h->h_top[k].seq;
     const uint8_t *b = h->h_tree.data() + (size_t)k * h->stride;
+    // byte item_byte(t) holds the row index q of the parent of sigma[t]; q = 0 root, q = j+1 node sigma[j]
+    std::vector<int> par_of(h->L, 0);
+    for (int t = 0; t < h->L; t++) {
+        const int q = b[item_byte(t, h->stride >> 2)];
+        if (q > h->L) { set_err("corrupt tree record: parent row %d at position %d", q, t); return LICHEE_ERR_STATE; }
+        par_of[t] = q == 0 ? 0 : h->sigma[q - 1];
+    }
     if (parent) {
         parent[0] = -1;
-        for (int t = 0; t < h->L; t++) parent[h->sigma[t]] = b[t];
+        for (int t = 0; t < h->L; t++) parent[h->sigma[t]] = par_of[t];
     }
     if (order) {
         // treeNodes: root first, then a preorder in which a node always follows its parent and the
         // children of one parent keep the canonical (sigma) order used for the sums.
         std::vector<std::vector<int>> ch(h->n);
-        for (int t = 0; t < h->L; t++) ch[b[t]].push_back(h->sigma[t]);
+        for (int t = 0; t < h->L; t++) ch[par_of[t]].push_back(h->sigma[t]);
         std::vector<int> stack{0};
         int w = 0;
         while (!stack.empty()) {

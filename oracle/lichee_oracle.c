@@ -312,8 +312,8 @@ int lichee_oracle_search(int n, int S, const int *adj_off, const int *adj_idx, c
  *   sums    : children of a parent are added in sigma order (checkConstraint, PHYTree.java:156-174,
  *             and the per-sample sums of computeErrorScore, PHYTree.java:214-233)
  *   score   : the positive terms (sum - VAF(parent))^2 are added with the device's fixed-shape
- *             reduction (per parent a 32-lane butterfly over samples, then a butterfly over the 128
- *             parent slots) instead of the reference's one-after-another order: a few ulp apart,
+ *             reduction (per parent a 32-lane butterfly over samples, then a butterfly over 128
+ *             parent slots, slot 0 = root, slot t+1 = sigma[t]) instead of the reference's one-after-another order: a few ulp apart,
  *             far inside the 1e-9 relative tolerance BASELINE.json states
  *   caps    : the first max_trees valid trees in this order
  * ------------------------------------------------------------------------------------------ */
@@ -337,7 +337,10 @@ static double butterfly32(double *v) {
 }
 static double canon_score(canon_t *c) {
     double E[128];
+    int slot[128];                       /* reduction slot of a node: 0 = root, t+1 = sigma[t] */
     memset(E, 0, sizeof(E));
+    slot[0] = 0;
+    for (int t = 0; t < c->L; t++) slot[c->sigma[t]] = t + 1;
     for (int p = 0; p < c->n; p++) {
         if (c->nch[p] == 0) continue;
         double t[64], lane[32];
@@ -349,7 +352,7 @@ static double canon_score(canon_t *c) {
             if (sum > a) t[i] = (sum - a) * (sum - a);
         }
         for (int l = 0; l < 32; l++) lane[l] = c->S > 32 ? t[l] + t[l + 32] : t[l];
-        E[p] = butterfly32(lane);
+        E[slot[p]] = butterfly32(lane);
     }
     double lane[32];
     for (int l = 0; l < 32; l++) lane[l] = (E[l] + E[l + 32]) + (E[l + 64] + E[l + 96]);

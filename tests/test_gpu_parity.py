@@ -87,6 +87,14 @@ def test_more_than_32_samples_two_per_lane(built):
     assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=1000, max_trees=100000)
 
 
+@pytest.mark.parametrize("n_clusters,n_samples", [(17, 7), (20, 20), (33, 12), (40, 20), (70, 33), (100, 48), (120, 64), (127, 64)])
+def test_every_item_width_and_the_named_shapes(built, n_clusters, n_samples):
+    """Item strides 16..128 bytes (the byte layout of a frontier item depends on it), including the
+    BASELINE shapes 40x20 and 120x64 and the size limits; capped so the CPU specification stays fast."""
+    net, prm = make_instance(n_clusters, n_samples, seed=n_clusters)
+    assert_matches_canonical(net.adj, net.aaf, prm.vaf_error_margin, num_save=200, max_trees=30000)
+
+
 def test_chunked_frontier_small_level_capacity(built):
     """A tiny level_capacity forces many depth-first chunks and partial emits; results must not move."""
     net, prm = make_instance(11, 4, seed=2)
