@@ -366,55 +366,59 @@ __device__ __forceinline__ double parent_excess(double s0, double s1, double a0,
     return butterfly_sum(t);
 }
 
+// At the last level the sum-rule check and the scoring share all their sums, so one kernel does
+// both: it writes the pass mask + count of every item (for the scan that numbers the valid trees)
+// and appends the trees that beat the threshold with a provisional sequence number; seq_fixup_kernel
+// turns that into the canonical one once the scan has run.
 template <int SPL>
 __global__ void __launch_bounds__(kThreads)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, long long item_base,
-            const uint4 *__restrict__ mask, const unsigned *__restrict__ off, long long seq_base,
-            long long max_trees, int part, TopMeta *meta, int num_save, Cand *__restrict__ cands,
-            long long cand_cap) {
+            uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out, int part, TopMeta *meta,
+            int num_save, Cand *__restrict__ cands, long long cand_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    __shared__ uint8_t cidx_s[kMaxN];          // candidate index of a row (valid where candq has the bit)
+    __shared__ unsigned candq_s[4];            // rows that are candidates for the last node
     const int level = net.L - 1;
+    const int k = net.ncand[level];
+    if (threadIdx.x < 4) candq_s[threadIdx.x] = 0;
     stage_network(net, level, vaf_s, cand_s);
+    if (threadIdx.x < k) {
+        const unsigned q = cand_s[threadIdx.x];
+        cidx_s[q] = (uint8_t)threadIdx.x;
+        atomicOr(&candq_s[q >> 5], 1u << (q & 31));
+    }
+    __syncthreads();
+    const unsigned candq[4] = {candq_s[0], candq_s[1], candq_s[2], candq_s[3]};
 
     const int lane = threadIdx.x & 31;
     const int SP = net.SP;
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const int wstride = net.stride >> 2;
-    const int rmax = level > 0 ? (level - 1) / (net.stride >> 2) : -1;
+    const int rmax = level > 0 ? (level - 1) / wstride : -1;
     const double xv0 = vaf_s[(level + 1) * SP + lane];
     const double xv1 = SPL == 2 ? vaf_s[(level + 1) * SP + 32 + lane] : 0.0;
     const double tau = meta->tau;
     const bool full = meta->count >= (unsigned)num_save;
+    // a tree can only enter the full list with sqrt(total) < tau; totals clearly above tau^2 skip the sqrt
+    const double tau2_hi = full ? __dmul_rn(__dmul_rn(tau, tau), 1.0 + 1e-12) : INFINITY;
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
 
     for (long long it = warp0; it < n_items; it += nwarps) {
-        const uint4 m4 = mask[it];
-        if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
-        long long seq = seq_base + (long long)off[it];
-        if (seq >= max_trees) continue;
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
-        const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
-
-        // rows that matter: parents present in the item, plus the passing choices for the last node
-        unsigned um[4], pq[4] = {0, 0, 0, 0};
+        unsigned um[4];
         parent_presence(w, rmax, um);
-        for (int g = 0; g < 4; g++) {
-            unsigned b = mw[g];
-            while (b) {
-                const unsigned q = cand_s[g * 32 + __ffs(b) - 1];
-                b &= b - 1;
-                pq[q >> 5] |= 1u << (q & 31);
-            }
-        }
-        // single pass: E[q] of the item without its last node and, for passing choices, E'[q] with
-        // the last node added.  Lane l keeps rows l, l+32, l+64, l+96 of both.
+        // single pass over the parents present in the item and the candidate parents of the last
+        // node: E[q] without the last node; for candidates the sum-rule check and E'[q] with it.
+        // Lane l keeps rows l, l+32, l+64, l+96.  pb* = pass bits by candidate index.
         double E0 = 0.0, E1 = 0.0, E2 = 0.0, E3 = 0.0, F0 = 0.0, F1 = 0.0, F2 = 0.0, F3 = 0.0;
+        unsigned pb0 = 0, pb1 = 0, pb2 = 0, pb3 = 0;
+#pragma unroll
         for (int g = 0; g < 4; g++) {
-            unsigned rows = um[g] | pq[g];
+            unsigned rows = um[g] | candq[g];
             while (rows) {
                 const int bq = __ffs(rows) - 1;
                 rows &= rows - 1;
@@ -424,10 +428,22 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 const double a0 = vaf_s[q * SP + lane], a1 = SPL == 2 ? vaf_s[q * SP + 32 + lane] : 0.0;
                 const double Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
                 double Fq = 0.0;
-                if ((pq[g] >> bq) & 1u) {
+                if ((candq[g] >> bq) & 1u) {
                     s0 = __dadd_rn(s0, xv0);
-                    if (SPL == 2) s1 = __dadd_rn(s1, xv1);
-                    Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                    bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
+                    if (SPL == 2) {
+                        s1 = __dadd_rn(s1, xv1);
+                        bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
+                    }
+                    if (!__any_sync(kFull, bad)) {
+                        Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                        const unsigned i = cidx_s[q];
+                        const unsigned bit = 1u << (i & 31);
+                        pb0 |= (i >> 5) == 0 ? bit : 0u;
+                        pb1 |= (i >> 5) == 1 ? bit : 0u;
+                        pb2 |= (i >> 5) == 2 ? bit : 0u;
+                        pb3 |= (i >> 5) == 3 ? bit : 0u;
+                    }
                 }
                 if (lane == bq) {
                     if (g == 0) { E0 = Eq; F0 = Fq; } else if (g == 1) { E1 = Eq; F1 = Fq; }
@@ -435,21 +451,26 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 }
             }
         }
+        if (lane == 0) {
+            mask_out[it] = make_uint4(pb0, pb1, pb2, pb3);
+            count_out[it] = __popc(pb0) + __popc(pb1) + __popc(pb2) + __popc(pb3);
+        }
 
         // one complete tree per passing choice: swap one slot, reduce
+        const unsigned mw[4] = {pb0, pb1, pb2, pb3};
+#pragma unroll
         for (int g = 0; g < 4; g++) {
             unsigned b = mw[g];
             while (b) {
                 const int i = g * 32 + __ffs(b) - 1;
                 b &= b - 1;
-                const long long my_seq = seq++;
-                if (my_seq >= max_trees) continue;
                 const unsigned q = cand_s[i];
                 const bool mine = lane == (int)(q & 31);
                 const int ps = q >> 5;
                 const double e0 = (mine && ps == 0) ? F0 : E0, e1 = (mine && ps == 1) ? F1 : E1;
                 const double e2 = (mine && ps == 2) ? F2 : E2, e3 = (mine && ps == 3) ? F3 : E3;
                 const double total = butterfly_sum(__dadd_rn(__dadd_rn(e0, e1), __dadd_rn(e2, e3)));
+                if (total > tau2_hi) continue;
                 const double score = __dsqrt_rn(total);
                 if (!full || score < tau) {
                     if (lane == 0) {
@@ -457,10 +478,10 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                         if ((long long)slot < cand_cap) {
                             Cand c;
                             c.score = score;
-                            c.seq = my_seq;
+                            c.seq = 0;
                             c.part = part;
                             c.origin = (unsigned)(item_base + it);
-                            c.pstar = q;
+                            c.pstar = q | ((unsigned)i << 8);
                             c.pad = 0;
                             cands[slot] = c;
                         }
@@ -469,6 +490,30 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             }
         }
     }
+}
+
+// Gives every candidate its canonical sequence number (rank among the valid trees) now that the
+// scan has numbered the items, and retires the ones beyond Parameters.MAX_NUM_TREES.
+__global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, const uint4 *__restrict__ mask,
+                                 const unsigned *__restrict__ off, long long seq_base, long long max_trees) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    Cand c = cands[t];
+    const long long it = (long long)c.origin - item_base;
+    const unsigned i = c.pstar >> 8;
+    const uint4 m4 = mask[it];
+    const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
+    unsigned rank = 0;
+    for (unsigned g = 0; g < (i >> 5); g++) rank += __popc(mw[g]);
+    rank += __popc(mw[i >> 5] & ((1u << (i & 31)) - 1u));
+    const long long seq = seq_base + (long long)off[it] + rank;
+    c.pstar &= 0xffu;
+    if (seq >= max_trees) {
+        c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu; c.pad = 1;
+    } else {
+        c.seq = seq;
+    }
+    cands[t] = c;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -600,7 +645,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
     }
 }
 
-__global__ void set_n_cand(TopMeta *meta, unsigned long long m) { meta->n_cand = m; }
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -830,17 +875,20 @@ int fetch_top(lichee_search *h) {
 }
 
 // Adds the kernel times of one finished chunk (event set `set`) to the statistics.
-// Boundaries: 0 start | 1 after check | 2 after scan | 3 after emit or leaf | 4 after select.
+// Boundaries: 0 start | 1 after check (or fused leaf) | 2 after scan | 3 after emit (leaf: after the
+// host read of the candidate count) | 4 after seq fix-up + select.
 int harvest_events(lichee_search *h, int set) {
     const int nb = h->evn[set];
     if (nb < 3) return LICHEE_OK;
     CK(cudaEventSynchronize(h->evk[set][nb - 1]));
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, h->evk[set][0], h->evk[set][1])); h->stats.kernel_ms[LICHEE_K_CHECK] += ms;
+    // a last-level chunk runs the fused check+score kernel where the others run the check kernel
+    CK(cudaEventElapsedTime(&ms, h->evk[set][0], h->evk[set][1]));
+    h->stats.kernel_ms[h->ev_leaf[set] ? LICHEE_K_LEAF : LICHEE_K_CHECK] += ms;
     CK(cudaEventElapsedTime(&ms, h->evk[set][1], h->evk[set][2])); h->stats.kernel_ms[LICHEE_K_SCAN] += ms;
-    if (nb > 3) {
+    if (nb > 3 && !h->ev_leaf[set]) {
         CK(cudaEventElapsedTime(&ms, h->evk[set][2], h->evk[set][3]));
-        h->stats.kernel_ms[h->ev_leaf[set] ? LICHEE_K_LEAF : LICHEE_K_EMIT] += ms;
+        h->stats.kernel_ms[LICHEE_K_EMIT] += ms;
     }
     if (nb > 4) { CK(cudaEventElapsedTime(&ms, h->evk[set][3], h->evk[set][4])); h->stats.kernel_ms[LICHEE_K_SELECT] += ms; }
     h->evn[set] = 0;
@@ -928,39 +976,45 @@ int run_search(lichee_search *h) {
         if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;   // the chunk before last
         h->ev_leaf[es] = leaf;
         CK(cudaEventRecord(h->evk[es][0], h->stream));
-        if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        const long long cand_cap = B * kcand;
+        if (!leaf) {
+            if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            st.kernel_launches[LICHEE_K_CHECK]++;
+            st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 20);
+        } else {
+            // last level: check and scoring fused
+            if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem_leaf, h->stream>>>(
+                h->net, items, B, h->head[lv], h->d_mask(), h->d_cnt(), R, h->d_meta(), h->prm.num_save,
+                h->d_cands(0), cand_cap);
+            CK(cudaGetLastError());
+            st.kernel_launches[LICHEE_K_LEAF]++;
+            st.kernel_bytes[LICHEE_K_LEAF] += B * (long long)(h->stride + 20);
+        }
         CK(cudaEventRecord(h->evk[es][1], h->stream));
         const unsigned long long limit = leaf ? ~0ull >> 1 : (unsigned long long)h->cap;
         if (launch_scan(h, B, limit) != LICHEE_OK) return LICHEE_ERR_CUDA;
         CK(cudaEventRecord(h->evk[es][2], h->stream));
         h->evn[es] = 3;
         st.num_launches += 4;
-        st.kernel_launches[LICHEE_K_CHECK]++;
         st.kernel_launches[LICHEE_K_SCAN] += 3;
-        st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 20);
         st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
         if (leaf) {
-            const long long cand_cap = B * kcand;
-            if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
-            leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem_leaf, h->stream>>>(
-                h->net, items, B, h->head[lv], h->d_mask(), h->d_off(), seq_base, h->prm.max_num_trees, R,
-                h->d_meta(), h->prm.num_save, h->d_cands(0), cand_cap);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(h->evk[es][3], h->stream));
-            st.num_launches++;
-            st.kernel_launches[LICHEE_K_LEAF]++;
-            st.kernel_bytes[LICHEE_K_LEAF] += B * (long long)(h->stride + 20);
             CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             long long m = (long long)std::min<unsigned long long>(h->h_meta->n_cand, (unsigned long long)cand_cap);
+            CK(cudaEventRecord(h->evk[es][3], h->stream));
             if (m > 0) {
+                seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], h->d_mask(),
+                                                                             h->d_off(), seq_base, h->prm.max_num_trees);
+                CK(cudaGetLastError());
+                st.num_launches++;
                 int src = 0;
                 if (run_tournament(h, m, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
-                if (src != 0) {   // survivors sit in the second buffer and may hold sentinel padding
-                    set_n_cand<<<1, 1, 0, h->stream>>>(h->d_meta(), (unsigned long long)m);
-                }
                 if (run_select(h, h->d_cands(src), m, h->level(lv), 0, nullptr, 0) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 st.kernel_bytes[LICHEE_K_SELECT] += (long long)sizeof(Cand) * (long long)h->h_meta->n_cand;
+            } else {
+                reset_n_cand<<<1, 1, 0, h->stream>>>(h->d_meta());
             }
             CK(cudaEventRecord(h->evk[es][4], h->stream));
             h->evn[es] = 5;
