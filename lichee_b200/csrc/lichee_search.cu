@@ -74,6 +74,7 @@ struct DevNet {
     const uint8_t *cand;     // [L][128]  candidate parents of sigma[t] as row indices q, in ascending NODE id
     const uint8_t *ncand;    // [L]
     const uint4 *static_ok;  // [L]       bit i: candidate i passes the sum rule when it has no other child
+    const double *leaf_static; // [128]   last level: excess E' of candidate i when the last node is its only child
     int n, S, SP, L, stride; // stride = bytes per frontier item (multiple of 16, <= 128)
     double margin;
 };
@@ -378,19 +379,25 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
-    __shared__ uint8_t cidx_s[kMaxN];          // candidate index of a row (valid where candq has the bit)
-    __shared__ unsigned candq_s[4];            // rows that are candidates for the last node
+    __shared__ double fstat_s[kMaxN];          // by row: E' of a candidate whose only child is the last node
+    __shared__ uint8_t cidx_s[kMaxN];          // by row: candidate index (valid where candq has the bit)
+    __shared__ unsigned candq_s[4], okq_s[4];  // rows that are candidates / that pass with no other child
     const int level = net.L - 1;
     const int k = net.ncand[level];
-    if (threadIdx.x < 4) candq_s[threadIdx.x] = 0;
+    if (threadIdx.x < 4) { candq_s[threadIdx.x] = 0; okq_s[threadIdx.x] = 0; }
     stage_network(net, level, vaf_s, cand_s);
     if (threadIdx.x < k) {
         const unsigned q = cand_s[threadIdx.x];
         cidx_s[q] = (uint8_t)threadIdx.x;
+        fstat_s[q] = net.leaf_static[threadIdx.x];
         atomicOr(&candq_s[q >> 5], 1u << (q & 31));
+        const uint4 so = net.static_ok[level];
+        const unsigned sw = (threadIdx.x >> 5) == 0 ? so.x : (threadIdx.x >> 5) == 1 ? so.y : (threadIdx.x >> 5) == 2 ? so.z : so.w;
+        if ((sw >> (threadIdx.x & 31)) & 1u) atomicOr(&okq_s[q >> 5], 1u << (q & 31));
     }
     __syncthreads();
     const unsigned candq[4] = {candq_s[0], candq_s[1], candq_s[2], candq_s[3]};
+    const unsigned okq[4] = {okq_s[0], okq_s[1], okq_s[2], okq_s[3]};
 
     const int lane = threadIdx.x & 31;
     const int SP = net.SP;
@@ -411,14 +418,18 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
         unsigned um[4];
         parent_presence(w, rmax, um);
-        // single pass over the parents present in the item and the candidate parents of the last
-        // node: E[q] without the last node; for candidates the sum-rule check and E'[q] with it.
-        // Lane l keeps rows l, l+32, l+64, l+96.  pb* = pass bits by candidate index.
-        double E0 = 0.0, E1 = 0.0, E2 = 0.0, E3 = 0.0, F0 = 0.0, F1 = 0.0, F2 = 0.0, F3 = 0.0;
-        unsigned pb0 = 0, pb1 = 0, pb2 = 0, pb3 = 0;
+        // Rows: E[q] = excess of parent q without the last node, F[q] = with it (passing candidates).
+        // Lane l keeps rows l, l+32, l+64, l+96.  passq = passing candidates by row.
+        double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned passq[4];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            unsigned rows = um[g] | candq[g];
+            // candidates with no child in this item: everything about them is static
+            const unsigned absent = candq[g] & ~um[g] & okq[g];
+            passq[g] = absent;
+            if ((absent >> lane) & 1u) F[g] = fstat_s[g * 32 + lane];
+            // parents present in the item
+            unsigned rows = um[g];
             while (rows) {
                 const int bq = __ffs(rows) - 1;
                 rows &= rows - 1;
@@ -427,7 +438,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
                 const double a0 = vaf_s[q * SP + lane], a1 = SPL == 2 ? vaf_s[q * SP + 32 + lane] : 0.0;
                 const double Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
-                double Fq = 0.0;
+                if (lane == bq) E[g] = Eq;
                 if ((candq[g] >> bq) & 1u) {
                     s0 = __dadd_rn(s0, xv0);
                     bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
@@ -436,52 +447,67 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                         bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
                     }
                     if (!__any_sync(kFull, bad)) {
-                        Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
-                        const unsigned i = cidx_s[q];
-                        const unsigned bit = 1u << (i & 31);
-                        pb0 |= (i >> 5) == 0 ? bit : 0u;
-                        pb1 |= (i >> 5) == 1 ? bit : 0u;
-                        pb2 |= (i >> 5) == 2 ? bit : 0u;
-                        pb3 |= (i >> 5) == 3 ? bit : 0u;
+                        const double Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                        if (lane == bq) F[g] = Fq;
+                        passq[g] |= 1u << bq;
                     }
-                }
-                if (lane == bq) {
-                    if (g == 0) { E0 = Eq; F0 = Fq; } else if (g == 1) { E1 = Eq; F1 = Fq; }
-                    else if (g == 2) { E2 = Eq; F2 = Fq; } else { E3 = Eq; F3 = Fq; }
                 }
             }
         }
-        if (lane == 0) {
-            mask_out[it] = make_uint4(pb0, pb1, pb2, pb3);
-            count_out[it] = __popc(pb0) + __popc(pb1) + __popc(pb2) + __popc(pb3);
-        }
-
-        // one complete tree per passing choice: swap one slot, reduce
-        const unsigned mw[4] = {pb0, pb1, pb2, pb3};
+        // pass mask by candidate index (canonical order of the trees of this item)
+        unsigned pb[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            unsigned b = mw[g];
+            const unsigned i = ((passq[g] >> lane) & 1u) ? cidx_s[g * 32 + lane] : 0xffu;
+#pragma unroll
+            for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
+        }
+        if (lane == 0) {
+            mask_out[it] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+            count_out[it] = __popc(pb[0]) + __popc(pb[1]) + __popc(pb[2]) + __popc(pb[3]);
+        }
+
+        // Base reduction over the 128 slots, remembering what each lane received at every stage: a
+        // tree differs from the base in one slot of one lane, so its total is that lane's partial
+        // pushed through the same five additions -- bit-identical to a full butterfly.
+        const double P = __dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3]));
+        double rcv[5];
+        {
+            double v = P;
+#pragma unroll
+            for (int st = 0; st < 5; st++) {
+                rcv[st] = __shfl_xor_sync(kFull, v, 16 >> st);
+                v = __dadd_rn(v, rcv[st]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            // this lane's partial with slot g swapped for F
+            const double A = g == 0 ? __dadd_rn(__dadd_rn(F[0], E[1]), __dadd_rn(E[2], E[3]))
+                           : g == 1 ? __dadd_rn(__dadd_rn(E[0], F[1]), __dadd_rn(E[2], E[3]))
+                           : g == 2 ? __dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(F[2], E[3]))
+                                    : __dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], F[3]));
+            double x = A;
+#pragma unroll
+            for (int st = 0; st < 5; st++) x = __dadd_rn(x, rcv[st]);
+            unsigned b = passq[g];
             while (b) {
-                const int i = g * 32 + __ffs(b) - 1;
+                const int bq = __ffs(b) - 1;
                 b &= b - 1;
-                const unsigned q = cand_s[i];
-                const bool mine = lane == (int)(q & 31);
-                const int ps = q >> 5;
-                const double e0 = (mine && ps == 0) ? F0 : E0, e1 = (mine && ps == 1) ? F1 : E1;
-                const double e2 = (mine && ps == 2) ? F2 : E2, e3 = (mine && ps == 3) ? F3 : E3;
-                const double total = butterfly_sum(__dadd_rn(__dadd_rn(e0, e1), __dadd_rn(e2, e3)));
+                const double total = __shfl_sync(kFull, x, bq);
                 if (total > tau2_hi) continue;
                 const double score = __dsqrt_rn(total);
                 if (!full || score < tau) {
                     if (lane == 0) {
                         const unsigned long long slot = atomicAdd(&meta->n_cand, 1ull);
                         if ((long long)slot < cand_cap) {
+                            const unsigned q = g * 32 + bq;
                             Cand c;
                             c.score = score;
                             c.seq = 0;
                             c.part = part;
                             c.origin = (unsigned)(item_base + it);
-                            c.pstar = q | ((unsigned)i << 8);
+                            c.pstar = q | ((unsigned)cidx_s[q] << 8);
                             c.pad = 0;
                             cands[slot] = c;
                         }
@@ -1226,12 +1252,38 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         }
         sok[t] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
     }
+    // last level, candidate whose only child is the last node: its excess E' through the device's
+    // fixed-shape reduction (lane value t[l] + t[l+32], xor-butterfly over 32 lanes), same IEEE operations
+    std::vector<double> lstat(kMaxN, 0.0);
+    if (h->L > 0) {
+        const int t = h->L - 1, v = h->sigma[t];
+        for (size_t i = 0; i < h->cands[t].size(); i++) {
+            const int p = h->cands[t][i];
+            volatile double term[64];
+            for (int s = 0; s < 64; s++) term[s] = 0.0;
+            for (int s = 0; s < S; s++) {
+                volatile double sum = 0.0 + vaf[(size_t)v * S + s];
+                volatile double a = vaf[(size_t)p * S + s];
+                if (sum > a) { volatile double d = sum - a; term[s] = d * d; }
+            }
+            volatile double lanev[32];
+            for (int l = 0; l < 32; l++) lanev[l] = term[l] + term[l + 32];
+            for (int d = 16; d > 0; d >>= 1) {
+                volatile double nx[32];
+                for (int l = 0; l < 32; l++) nx[l] = lanev[l] + lanev[l ^ d];
+                for (int l = 0; l < 32; l++) lanev[l] = nx[l];
+            }
+            lstat[i] = lanev[0];
+        }
+    }
 #define CKE(call) do { if ((call) != LICHEE_OK) { lichee_search_destroy(h); return LICHEE_ERR_CUDA; } } while (0)
-    // one buffer for the network: [vaf | static_ok | cand | ncand]
-    const size_t o_sok = vp.size() * sizeof(double), o_cand = o_sok + sok.size() * sizeof(uint4), o_ncand = o_cand + cd.size();
+    // one buffer for the network: [vaf | leaf_static | static_ok | cand | ncand]
+    const size_t o_ls = vp.size() * sizeof(double), o_sok = o_ls + lstat.size() * sizeof(double);
+    const size_t o_cand = o_sok + sok.size() * sizeof(uint4), o_ncand = o_cand + cd.size();
     CKE(ensure(h, h->b_net, o_ncand + nc.size()));
     char *nb = static_cast<char *>(h->b_net.p);
     CKD(cudaMemcpyAsync(nb, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(nb + o_ls, lstat.data(), lstat.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_sok, sok.data(), sok.size() * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
@@ -1249,6 +1301,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     }
     h->net.vaf = reinterpret_cast<const double *>(nb);
     h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
+    h->net.leaf_static = reinterpret_cast<const double *>(nb + o_ls);
     h->net.cand = reinterpret_cast<const uint8_t *>(nb + o_cand);
     h->net.ncand = reinterpret_cast<const uint8_t *>(nb + o_ncand);
     h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
