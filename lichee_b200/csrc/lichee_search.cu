@@ -296,6 +296,47 @@ scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
     if (best) atomicMax(&out->fit, best);
 }
 
+// Single-launch variant for narrow chunks (the first descent, small networks): one block, each
+// thread owns a contiguous run.  Wider chunks use the three-kernel tiled scan, which is faster there.
+constexpr int kScanSingleThreads = 1024;
+constexpr long long kScanSingleMax = 4096;
+
+__global__ void __launch_bounds__(kScanSingleThreads)
+scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long long n, unsigned long long limit,
+            ScanOut *out) {
+    __shared__ unsigned warp_tot[kScanSingleThreads / 32];
+    __shared__ unsigned long long best_s;
+    if (threadIdx.x == 0) best_s = 0;
+    const long long per = (n + kScanSingleThreads - 1) / kScanSingleThreads;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < n ? lo + per : n;
+    unsigned run = 0;
+    for (long long i = lo; i < hi; i++) run += cnt[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+    for (int i = 0; i < kScanSingleThreads / 32; i++) {
+        if (i < wid) woff += warp_tot[i];
+        total += warp_tot[i];
+    }
+    unsigned long long ex = woff + inc - run, best = 0;
+    for (long long i = lo; i < hi; i++) {
+        off[i] = (unsigned)ex;
+        ex += cnt[i];
+        if (ex <= limit) best = ((unsigned long long)(i + 1) << 32) | ex;
+    }
+    if (best) atomicMax(&best_s, best);
+    __syncthreads();
+    if (threadIdx.x == 0) { out->fit = best_s; out->total = total; }
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel 3: emit.  One warp per parent item writes its surviving children, 128 coalesced bytes
 // per child, at the offsets the scan assigned (so children appear in canonical order).
@@ -625,29 +666,64 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
             e[t] = sentinel;
         }
     }
-    __syncthreads();
-    for (unsigned long long base = 0; base < m; base += kSelTile) {
-        for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
-            e[kSelTile + t] = base + t < m ? cands[base + t] : sentinel;
-        __syncthreads();
-        bitonic_sort_2048(e);
-    }
-    // candidates may contain sentinel padding written by the tournament: count the real entries
     __shared__ unsigned real_n;
     if (threadIdx.x == 0) real_n = 0;
     __syncthreads();
-    {
+    Cand *res = e;
+    if (m <= (unsigned long long)kSelTile) {
+        // Common case, a handful of new candidates: rank-merge.  Keys (score, part, seq) are unique,
+        // so the final position of an entry is the number of entries smaller than it.
+        Cand *fresh = e + kSelTile, *out = e + 2 * kSelTile;
+        const int mm = (int)m;
+        const int t = threadIdx.x;
+        fresh[t] = t < mm ? cands[t] : sentinel;
+        out[t] = sentinel;
+        __syncthreads();
+        const Cand mine_old = e[t], mine_new = fresh[t];
+        const bool has_old = (unsigned)t < count, has_new = t < mm && mine_new.pad == 0;
+        unsigned below_old = 0, below_new = 0;      // fresh entries smaller than my old / my new entry
+        for (int j = 0; j < mm; j++) {
+            const Cand c = fresh[j];
+            if (c.pad) continue;
+            below_old += cand_less(c, mine_old);
+            below_new += cand_less(c, mine_new);
+        }
+        if (has_new) {
+            int lo = 0, hi = (int)count;            // old entries smaller than my new entry
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cand_less(e[mid], mine_new)) lo = mid + 1; else hi = mid;
+            }
+            const unsigned pos = (unsigned)lo + below_new;
+            if (pos < (unsigned)kSelTile) out[pos] = mine_new;
+            atomicAdd(&real_n, 1u);
+        }
+        if (has_old) {
+            const unsigned pos = (unsigned)t + below_old;
+            if (pos < (unsigned)kSelTile) out[pos] = mine_old;
+            atomicAdd(&real_n, 1u);
+        }
+        __syncthreads();
+        res = out;
+    } else {
+        for (unsigned long long base = 0; base < m; base += kSelTile) {
+            for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
+                e[kSelTile + t] = base + t < m ? cands[base + t] : sentinel;
+            __syncthreads();
+            bitonic_sort_2048(e);
+        }
+        // candidates may contain sentinel padding written by the tournament: count the real entries
         unsigned mine = 0;
         for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) mine += e[t].pad == 0;
         if (mine) atomicAdd(&real_n, mine);
+        __syncthreads();
     }
-    __syncthreads();
     const unsigned newc = real_n < (unsigned)num_save ? real_n : (unsigned)num_save;
     // gather parent bytes of the survivors
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int wl = item_byte(last_level, wstride) >> 2, sh = 8 * (item_byte(last_level, wstride) & 3);
     for (unsigned t = wid; t < newc; t += kSelThreads / 32) {
-        const Cand c = e[t];
+        const Cand c = res[t];
         unsigned w = 0xffffffffu;
         if (lane < wstride) {
             if (c.origin & 0x80000000u) {
@@ -662,11 +738,11 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
             tree_next[(size_t)t * wstride + lane] = w;
         }
     }
-    for (int t = threadIdx.x; t < (int)newc; t += kSelThreads) top_next[t] = e[t];
+    for (int t = threadIdx.x; t < (int)newc; t += kSelThreads) top_next[t] = res[t];
     __syncthreads();
     if (threadIdx.x == 0) {
         meta->count = newc;
-        meta->tau = newc >= (unsigned)num_save ? e[newc - 1].score : INFINITY;
+        meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
     }
 }
@@ -843,10 +919,18 @@ int launch_check(lichee_search *h, int lv, const unsigned *items, long long n_it
 }
 
 int launch_scan(lichee_search *h, long long n_items, unsigned long long limit) {
-    const int tiles = (int)((n_items + kScanTile - 1) / kScanTile);
-    scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items);
-    scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile(), tiles, h->d_scan());
-    scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items, limit, h->d_scan());
+    if (n_items <= kScanSingleMax) {
+        scan_single<<<1, kScanSingleThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), n_items, limit, h->d_scan());
+        h->stats.num_launches += 1;
+        h->stats.kernel_launches[LICHEE_K_SCAN] += 1;
+    } else {
+        const int tiles = (int)((n_items + kScanTile - 1) / kScanTile);
+        scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items);
+        scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile(), tiles, h->d_scan());
+        scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items, limit, h->d_scan());
+        h->stats.num_launches += 3;
+        h->stats.kernel_launches[LICHEE_K_SCAN] += 3;
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
     return LICHEE_OK;
@@ -855,7 +939,7 @@ int launch_scan(lichee_search *h, long long n_items, unsigned long long limit) {
 // Final selection: merge `m_hint` candidates (already bounded by the caller) into the ranked list.
 int run_select(lichee_search *h, const Cand *cands, long long cand_cap, const unsigned *leaf_items, int external,
                const unsigned char *records, long long record_bytes) {
-    const size_t sm = sizeof(Cand) * 2 * kSelTile;
+    const size_t sm = sizeof(Cand) * 3 * kSelTile;
     select_kernel<<<1, kSelThreads, sm, h->stream>>>(h->d_meta(), h->prm.num_save, cands, cand_cap,
                                                      h->d_top(h->flip), h->d_top(h->flip ^ 1),
                                                      h->d_tree(h->flip), h->d_tree(h->flip ^ 1), leaf_items,
@@ -872,7 +956,7 @@ int run_select(lichee_search *h, const Cand *cands, long long cand_cap, const un
 int run_tournament(lichee_search *h, long long &m, int &src) {
     src = 0;
     const size_t sm = sizeof(Cand) * 2 * kSelTile;
-    while (m > kSelPerBlock) {
+    while (m > kSelTile) {
         const long long blocks = (m + kSelPerBlock - 1) / kSelPerBlock;
         if (ensure(h, h->b_cands[src ^ 1], sizeof(Cand) * (size_t)blocks * kSelTile) != LICHEE_OK) return LICHEE_ERR_CUDA;
         select_reduce_kernel<<<(int)blocks, kSelThreads, sm, h->stream>>>(h->d_cands(src), m, h->d_cands(src ^ 1));
@@ -1022,13 +1106,13 @@ int run_search(lichee_search *h) {
         if (launch_scan(h, B, limit) != LICHEE_OK) return LICHEE_ERR_CUDA;
         CK(cudaEventRecord(h->evk[es][2], h->stream));
         h->evn[es] = 3;
-        st.num_launches += 4;
-        st.kernel_launches[LICHEE_K_SCAN] += 3;
+        st.num_launches += 1;
         st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
         if (leaf) {
             CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             long long m = (long long)std::min<unsigned long long>(h->h_meta->n_cand, (unsigned long long)cand_cap);
+            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%llu tau=%.17g count=%u\n", B, m, h->h_scan->total, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
             if (m > 0) {
                 seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], h->d_mask(),
@@ -1312,7 +1396,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_leaf));
     CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_leaf));
-    CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
+    CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 3 * kSelTile)));
     CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
 #undef CKE
     CKD(cudaStreamSynchronize(h->stream));
