@@ -80,13 +80,14 @@ def java_string_hash(s):
     return h
 
 
-def java_hashmap_key_order(keys_in_insertion_order):
-    """Iteration order of java.util.HashMap<String,?>.keySet() for keys inserted in the given
-    order and never removed before the final table size is reached (bins stay linked lists for
-    < 8 collisions; resize preserves relative order inside a bin)."""
+def java_hashmap_key_order(keys_in_insertion_order, max_size=0):
+    """Iteration order of java.util.HashMap<String,?>.keySet(): buckets in index order, insertion
+    order inside a bucket (bins stay linked lists for < 8 collisions; a resize preserves the
+    relative order inside a bin).  The table doubles when size exceeds 0.75*capacity and never
+    shrinks, so `max_size` = the largest number of keys the map ever held."""
     keys = list(keys_in_insertion_order)
     cap = 16
-    while len(keys) > 0.75 * cap:
+    while max(len(keys), max_size) > 0.75 * cap:
         cap *= 2
     def spread(h):
         return (h ^ (h >> 16)) & 0xFFFFFFFF
@@ -166,10 +167,14 @@ def build_groups(path, prm: Params, normal_sample=0):
     emulated key order as well."""
     names, somatic, ambiguous, tag2snvs, insertion = load_snv_file(path, prm, normal_sample)
     S = len(names)
+    hwm = [len(insertion)]                       # high-water mark of tag2SNVs.size()
+    def hm_order(keys):                          # iteration order of tag2SNVs.keySet()
+        hwm[0] = max(hwm[0], len(keys))
+        return java_hashmap_key_order(keys, hwm[0])
     # small groups -> ambiguous
-    small = [t for t in java_hashmap_key_order(insertion)
+    small = [t for t in hm_order(insertion)
              if len(tag2snvs[t]) < prm.min_group_profile_support]
-    for t in java_hashmap_key_order(insertion):
+    for t in hm_order(insertion):
         if t in small:
             ambiguous.extend(tag2snvs[t])
     for t in small:
@@ -178,7 +183,7 @@ def build_groups(path, prm: Params, normal_sample=0):
     # assignAmbiguousSNVs
     if ambiguous:
         all1, all0 = '1' * S, '0' * S
-        targets = java_hashmap_key_order(insertion)
+        targets = hm_order(insertion)
         if all0 not in tag2snvs:
             targets.append(all0)
         targets.append(all1)
@@ -248,7 +253,7 @@ def build_groups(path, prm: Params, normal_sample=0):
                     adj[t].append(snv)
         while rest:
             mx, mset = 0, ""
-            for t in java_hashmap_key_order([x for x in ainsert if x in adj]):
+            for t in java_hashmap_key_order([x for x in ainsert if x in adj], len(ainsert)):
                 if len(adj[t]) > mx:
                     mx, mset = len(adj[t]), t
             if mx <= 1:
@@ -292,7 +297,7 @@ def build_groups(path, prm: Params, normal_sample=0):
         if '1' not in t or len(tag2snvs[t]) < prm.min_snvs_per_group:
             del tag2snvs[t]
             insertion.remove(t)
-    order = java_hashmap_key_order(insertion)
+    order = hm_order(insertion)
     robust = {}
     for t in order:
         nr = sum(1 for e in tag2snvs[t] if e.robust)
