@@ -94,6 +94,35 @@ class ClockSampler:
         return out
 
 
+def bundled_search_times(lichee_b200, with_cpu):
+    """-build search wall time on the bundled ccRCC / HGSC networks (BASELINE configs[0..2], README
+    settings, committed fixtures): end to end through the public API from host arrays, median of 5,
+    next to the CPU port of the reference search.  These searches are a handful of trees: they
+    measure launch latency, not throughput."""
+    path = os.path.join(ROOT, "tests", "golden", "networks_bundled.json")
+    if not os.path.exists(path):
+        return None
+    out = {}
+    for e in json.load(open(path)):
+        if e["clustering"] != "single" or e["complete_edges"]:
+            continue
+        adj, vaf = e["adj"], np.array(e["aaf"])
+        ts = []
+        for _ in range(6):
+            t0 = time.perf_counter()
+            s = lichee_b200.LineageSearch(adj, vaf, e["vaf_error_margin"], num_save=100 if "hgsc" in e["dataset"] else 1)
+            st = s.run(); s.trees(); s.close()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        rec = {"nodes": len(adj), "valid_trees": int(st.num_trees), "gpu_e2e_ms": round(statistics.median(ts[1:]), 3)}
+        if with_cpu:
+            import oracle
+            t0 = time.perf_counter()
+            oracle.search(adj, vaf, e["vaf_error_margin"], top_s=100)
+            rec["cpu_port_ms"] = round(1e3 * (time.perf_counter() - t0), 3)
+        out[e["dataset"]] = rec
+    return out
+
+
 def run_reference(args):
     """Reference arm: literal CPU port of PHYNetwork.grow on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -275,6 +304,8 @@ def main():
             "kernel_launches_per_step": {K[i]: nl[i] / args.steps for i in range(5)},
             "device_ms_per_step": sum(s.kernel_ms_total for s in stats) / args.steps,
         }
+        if world == 1:
+            line["bundled_datasets_build_search_ms"] = bundled_search_times(lichee_b200, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             t0 = time.perf_counter()

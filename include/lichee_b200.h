@@ -120,6 +120,11 @@ int lichee_search_get_stats(const lichee_search *h, lichee_search_stats *out);
 int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int32_t *parent,
                            int32_t *order, int64_t *seq);
 
+/* Ranked trees first .. first+count-1 in one call: scores[count], parents[count*n_nodes],
+ * orders[count*n_nodes], seqs[count] (any output may be NULL). */
+int lichee_search_get_trees(const lichee_search *h, int32_t first, int32_t count, double *scores,
+                            int32_t *parents, int32_t *orders, int64_t *seqs);
+
 /* Multi-GPU merge: raw ranked list of this handle (for an allgather) and its inverse.
  * A record is lichee_record_bytes(h) bytes: {double score; int64 seq; int32 part; int32 pad;
  * uint8 parent_of_position[stride]}.  Records stay in DEVICE memory when `device_ptr` is

@@ -22,7 +22,7 @@ STATUS_GROW_CAP = 2
 
 EXPORTED_SYMBOLS = [
     "lichee_default_params", "lichee_search_create", "lichee_search_run", "lichee_search_get_stats",
-    "lichee_search_get_tree", "lichee_record_bytes", "lichee_search_export_ranked",
+    "lichee_search_get_tree", "lichee_search_get_trees", "lichee_record_bytes", "lichee_search_export_ranked",
     "lichee_search_merge_ranked", "lichee_search_get_order", "lichee_search_destroy",
     "lichee_get_lineage_trees", "lichee_last_error", "lichee_version", "lichee_device_count",
 ]
@@ -82,6 +82,8 @@ def lib():
         L.lichee_search_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(SearchStats)]
         L.lichee_search_get_tree.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]
+        L.lichee_search_get_trees.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.lichee_search_export_ranked.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.lichee_search_merge_ranked.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int]
         L.lichee_search_get_order.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -118,16 +120,32 @@ class Parameters:
 
 
 class PHYTree:
-    """Ranked spanning tree returned by the device (PHYTree.java:44-54)."""
+    """Ranked spanning tree returned by the device (PHYTree.java:44-54).  treeNodes / treeEdges are
+    rebuilt on first use from the parent and insertion-order arrays the ABI returns."""
 
     def __init__(self, score, parent, order, seq):
         self.errorScore = float(score)
-        self.parent = [int(x) for x in parent]
-        self.treeNodes = [int(x) for x in order if x >= 0]
+        self._parent = parent
+        self._order = order
         self.seq = int(seq)
-        self.treeEdges = {}
-        for v in self.treeNodes[1:]:
-            self.treeEdges.setdefault(self.parent[v], []).append(v)
+        self._edges = None
+
+    @property
+    def parent(self):
+        return [int(x) for x in self._parent]
+
+    @property
+    def treeNodes(self):
+        return [int(x) for x in self._order if x >= 0]
+
+    @property
+    def treeEdges(self):
+        if self._edges is None:
+            self._edges = {}
+            par = self._parent
+            for v in self.treeNodes[1:]:
+                self._edges.setdefault(int(par[v]), []).append(v)
+        return self._edges
 
     def getErrorScore(self):
         return self.errorScore
@@ -186,7 +204,16 @@ class LineageSearch:
         return PHYTree(score.value, par, order, seq.value)
 
     def trees(self):
-        return [self.tree(k) for k in range(self.stats().num_saved)]
+        m = int(self.stats().num_saved)
+        if m == 0:
+            return []
+        sc = np.zeros(m, dtype=np.float64)
+        par = np.zeros((m, self.n), dtype=np.int32)
+        order = np.zeros((m, self.n), dtype=np.int32)
+        seq = np.zeros(m, dtype=np.int64)
+        _ck(lib().lichee_search_get_trees(self._h, 0, m, sc.ctypes.data, par.ctypes.data, order.ctypes.data,
+                                          seq.ctypes.data))
+        return [PHYTree(sc[k], par[k], order[k], seq[k]) for k in range(m)]
 
     def record_bytes(self):
         return int(lib().lichee_record_bytes(self._h))

@@ -836,6 +836,29 @@ struct DevicePool {
 };
 DevicePool g_pool;
 
+// Streams, events and the pinned read-back block are pooled as well: creating them costs tens of
+// milliseconds, more than a whole search of a real-data network.
+struct DevCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk[2][6] = {};
+    void *pinned = nullptr;
+};
+struct CtxPool {
+    std::mutex mu;
+    std::multimap<int, DevCtx> free_list;
+    bool attrs_set[64] = {};
+    bool get(int dev, DevCtx &c) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_list.find(dev);
+        if (it == free_list.end()) return false;
+        c = it->second;
+        free_list.erase(it);
+        return true;
+    }
+    void put(int dev, const DevCtx &c) { std::lock_guard<std::mutex> g(mu); free_list.insert({dev, c}); }
+};
+CtxPool g_ctx;
+
 struct DevBuf {              // one growable device buffer owned by a handle
     void *p = nullptr;
     size_t bytes = 0;
@@ -1217,11 +1240,12 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_mask); give_back(h, h->b_cnt); give_back(h, h->b_off); give_back(h, h->b_tile);
     give_back(h, h->b_small);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
-    if (h->h_scan) cudaFreeHost(h->h_scan);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) if (h->evk[a][b]) cudaEventDestroy(h->evk[a][b]);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream) {
+        DevCtx c;
+        c.stream = h->stream; c.ev0 = h->ev0; c.ev1 = h->ev1; c.pinned = h->h_scan;
+        for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) c.evk[x][y] = h->evk[x][y];
+        g_ctx.put(h->device, c);
+    }
     delete h;
     return LICHEE_OK;
 }
@@ -1308,9 +1332,18 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         }                                                                                          \
     } while (0)
     CKD(cudaSetDevice(h->device));
-    CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
-    for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
+    {
+        DevCtx c;
+        if (g_ctx.get(h->device, c)) {
+            h->stream = c.stream; h->ev0 = c.ev0; h->ev1 = c.ev1; h->h_scan = static_cast<ScanOut *>(c.pinned);
+            for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) h->evk[x][y] = c.evk[x][y];
+        } else {
+            CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
+            for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
+            CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta)));
+        }
+    }
     const int Lp = std::max(1, h->L);
     // row index q of every node: 0 = root, t+1 = sigma[t]
     std::vector<int> qof(n, 0);
@@ -1377,7 +1410,6 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
     CKE(ensure(h, h->b_small, 256));
-    CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta)));
     h->h_meta = reinterpret_cast<TopMeta *>(h->h_scan + 1);
     for (int i = 0; i < 2; i++) {
         CKE(ensure(h, h->b_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
@@ -1392,12 +1424,17 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->net.margin = params->vaf_error_margin;
     h->smem = (size_t)n * h->SP * sizeof(double) + kMaxN;
     h->smem_leaf = h->smem;
-    CKD(cudaFuncSetAttribute(check_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_leaf));
-    CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_leaf));
-    CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 3 * kSelTile)));
-    CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
+    if (h->device >= 0 && h->device < 64 && !g_ctx.attrs_set[h->device]) {
+        // opt in to the largest dynamic shared memory any network needs (128 rows x 64 samples)
+        const int mx = kMaxN * 64 * (int)sizeof(double) + kMaxN;
+        CKD(cudaFuncSetAttribute(check_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 3 * kSelTile)));
+        CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
+        g_ctx.attrs_set[h->device] = true;
+    }
 #undef CKE
     CKD(cudaStreamSynchronize(h->stream));
 #undef CKD
@@ -1459,6 +1496,18 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
             for (auto it = ch[u].rbegin(); it != ch[u].rend(); ++it) stack.push_back(*it);
         }
         for (; w < h->n; w++) order[w] = -1;
+    }
+    return LICHEE_OK;
+}
+
+int lichee_search_get_trees(const lichee_search *h, int32_t first, int32_t count, double *scores,
+                            int32_t *parents, int32_t *orders, int64_t *seqs) {
+    if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
+    for (int32_t k = 0; k < count; k++) {
+        const int rc = lichee_search_get_tree(h, first + k, scores ? scores + k : nullptr,
+                                              parents ? parents + (size_t)k * h->n : nullptr,
+                                              orders ? orders + (size_t)k * h->n : nullptr, seqs ? seqs + k : nullptr);
+        if (rc != LICHEE_OK) return rc;
     }
     return LICHEE_OK;
 }
