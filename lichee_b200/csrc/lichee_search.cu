@@ -99,6 +99,7 @@ struct TopMeta {             // device-resident state of the ranked list
     unsigned pad;
     double tau;              // score of the worst held tree once the list is full, else +inf
     unsigned long long n_cand;  // candidates appended by the current leaf launch
+    unsigned long long n_valid; // valid complete trees counted by the current leaf launch
 };
 
 struct ScanOut {             // written by the scan, read back by the host once per chunk
@@ -454,6 +455,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     const double tau2_hi = full ? __dmul_rn(__dmul_rn(tau, tau), 1.0 + 1e-12) : INFINITY;
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+    unsigned long long my_valid = 0;
 
     for (long long it = warp0; it < n_items; it += nwarps) {
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
@@ -503,9 +505,13 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
 #pragma unroll
             for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
         }
-        if (lane == 0) {
-            mask_out[it] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
-            count_out[it] = __popc(pb[0]) + __popc(pb[1]) + __popc(pb[2]) + __popc(pb[3]);
+        {
+            const unsigned cnt = __popc(pb[0]) + __popc(pb[1]) + __popc(pb[2]) + __popc(pb[3]);
+            my_valid += cnt;
+            if (lane == 0) {
+                mask_out[it] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                count_out[it] = cnt;
+            }
         }
 
         // Base reduction over the 128 slots, remembering what each lane received at every stage: a
@@ -557,6 +563,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             }
         }
     }
+    if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
 }
 
 // Gives every candidate its canonical sequence number (rank among the valid trees) now that the
@@ -744,16 +751,18 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->count = newc;
         meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
+        meta->n_valid = 0;
     }
 }
 
-__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; }
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
     meta->pad = 0;
     meta->tau = INFINITY;
     meta->n_cand = 0;
+    meta->n_valid = 0;
 }
 
 // unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
@@ -1125,18 +1134,27 @@ int run_search(lichee_search *h) {
             st.kernel_bytes[LICHEE_K_LEAF] += B * (long long)(h->stride + 20);
         }
         CK(cudaEventRecord(h->evk[es][1], h->stream));
-        const unsigned long long limit = leaf ? ~0ull >> 1 : (unsigned long long)h->cap;
-        if (launch_scan(h, B, limit) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        if (!leaf) {
+            if (launch_scan(h, B, (unsigned long long)h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
+        }
         CK(cudaEventRecord(h->evk[es][2], h->stream));
         h->evn[es] = 3;
         st.num_launches += 1;
-        st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
+        long long leaf_total = 0;
         if (leaf) {
+            // the kernel counted its valid trees; the scan that numbers them is only needed when
+            // some of them beat the threshold (most chunks: none)
             CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             long long m = (long long)std::min<unsigned long long>(h->h_meta->n_cand, (unsigned long long)cand_cap);
-            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%llu tau=%.17g count=%u\n", B, m, h->h_scan->total, h->h_meta->tau, h->h_meta->count);
+            leaf_total = (long long)h->h_meta->n_valid;
+            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
+            if (m > 0) {
+                if (launch_scan(h, B, ~0ull >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
+            }
             if (m > 0) {
                 seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], h->d_mask(),
                                                                              h->d_off(), seq_base, h->prm.max_num_trees);
@@ -1153,7 +1171,7 @@ int run_search(lichee_search *h) {
             h->evn[es] = 5;
             // widen the next leaf launch once the threshold rejects most trees
             if ((long long)h->h_meta->n_cand * 8 < leaf_ramp) leaf_ramp = std::min(leaf_ramp * 4, h->cap);
-            const long long total = (long long)h->h_scan->total;
+            const long long total = leaf_total;
             st.num_checks += B * kcand;
             st.num_grow_calls += total;
             st.frontier_bytes += B * (long long)h->stride;
