@@ -755,6 +755,87 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Radix pre-selection for long candidate lists (bursts: a chunk that enters a better region of the
+// search space beats a stale threshold with 10^5-10^6 trees).  Scores are non-negative doubles, so
+// their bit patterns order like unsigned integers: sixteen 8-bit passes over (score bits, seq) find
+// the num_save-th smallest key exactly, then the candidates at or below it are compacted for the
+// rank-merge.  O(m), where
+// the tournament of bitonic sorts is O(m log^2).
+// ------------------------------------------------------------------------------------------
+struct RadixState {
+    unsigned long long prefix[2];   // decided high bits of the k-th smallest key: [0] score bits, [1] seq
+    unsigned long long k;           // rank still to find inside the current prefix bucket
+    unsigned hist[256];
+    unsigned long long kept;        // candidates compacted
+};
+
+__global__ void radix_init(RadixState *st, unsigned long long k) {
+    st->prefix[0] = st->prefix[1] = 0;
+    st->k = k;
+    st->kept = 0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) st->hist[i] = 0;
+}
+
+// pass 0..7: bytes of the score (high to low); pass 8..15: bytes of seq among candidates whose score
+// equals the selected one.  (part is constant inside one handle's candidate list.)
+__global__ void __launch_bounds__(256)
+radix_hist(const Cand *__restrict__ cands, long long m, RadixState *st, int pass) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int word = pass >> 3, shift = 56 - 8 * (pass & 7);
+    const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
+    const unsigned long long himask = (pass & 7) == 0 ? 0ull : ~0ull << (shift + 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const Cand c = cands[i];
+        if (c.pad) continue;
+        const unsigned long long k0 = (unsigned long long)__double_as_longlong(c.score), k1 = (unsigned long long)c.seq;
+        if (word == 0) {
+            if ((k0 & himask) == (p0 & himask)) atomicAdd(&h[(k0 >> shift) & 0xff], 1u);
+        } else if (k0 == p0 && (k1 & himask) == (p1 & himask)) {
+            atomicAdd(&h[(k1 >> shift) & 0xff], 1u);
+        }
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void radix_pick(RadixState *st, int pass) {
+    if (threadIdx.x == 0) {
+        const int word = pass >> 3, shift = 56 - 8 * (pass & 7);
+        unsigned long long k = st->k, run = 0;
+        int b = 0;
+        for (; b < 256; b++) {
+            if (run + st->hist[b] >= k) break;
+            run += st->hist[b];
+        }
+        if (b == 256) {                               // fewer than k candidates: keep everything
+            st->prefix[word] |= 0xffull << shift;
+            st->k = 1ull << 62;
+        } else {
+            st->prefix[word] |= (unsigned long long)b << shift;
+            st->k = k - run;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) st->hist[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+radix_compact(const Cand *__restrict__ cands, long long m, RadixState *st, Cand *__restrict__ out, long long out_cap) {
+    const unsigned long long t0 = st->prefix[0], t1 = st->prefix[1];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const Cand c = cands[i];
+        if (c.pad) continue;
+        const unsigned long long k0 = (unsigned long long)__double_as_longlong(c.score), k1 = (unsigned long long)c.seq;
+        if (k0 < t0 || (k0 == t0 && k1 <= t1)) {
+            const unsigned long long slot = atomicAdd(&st->kept, 1ull);
+            if ((long long)slot < out_cap) out[slot] = c;
+        }
+    }
+}
+
 __global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; }
 
 __global__ void init_meta(TopMeta *meta) {
@@ -889,7 +970,7 @@ struct lichee_search {
     std::vector<DevBuf> b_level;             // frontier buffers, grown on demand
     std::vector<long long> head, tail;
     long long cap = 0;                       // upper bound on items per level buffer
-    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_cands[2], b_top[2], b_tree[2];
+    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_cands[2], b_top[2], b_tree[2];
     ScanOut *h_scan = nullptr;               // pinned
     TopMeta *h_meta = nullptr;               // pinned
     int flip = 0;
@@ -980,6 +1061,34 @@ int run_select(lichee_search *h, const Cand *cands, long long cand_cap, const un
     h->flip ^= 1;
     h->stats.num_launches++;
     h->stats.kernel_launches[LICHEE_K_SELECT]++;
+    return LICHEE_OK;
+}
+
+// Radix pre-selection: on return the (at most kSelTile) survivors sit in b_cands[1] and m is their
+// count; returns LICHEE_OK with used=false when ties at the threshold overflow the rank-merge tile
+// (then the caller falls back to the tournament on the untouched list in b_cands[0]).
+int run_radix_select(lichee_search *h, long long &m, bool &used) {
+    used = false;
+    if (ensure(h, h->b_radix, sizeof(RadixState)) != LICHEE_OK ||
+        ensure(h, h->b_cands[1], sizeof(Cand) * (size_t)kSelTile) != LICHEE_OK)
+        return LICHEE_ERR_CUDA;
+    RadixState *st = static_cast<RadixState *>(h->b_radix.p);
+    const int grid = (int)std::min<long long>((m + 255) / 256, 148 * 8);
+    radix_init<<<1, 256, 0, h->stream>>>(st, (unsigned long long)h->prm.num_save);
+    for (int pass = 0; pass < 16; pass++) {
+        radix_hist<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, pass);
+        radix_pick<<<1, 256, 0, h->stream>>>(st, pass);
+    }
+    radix_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, h->d_cands(1), (long long)kSelTile);
+    CK(cudaGetLastError());
+    h->stats.num_launches += 34;
+    h->stats.kernel_launches[LICHEE_K_SELECT] += 34;
+    unsigned long long kept = 0;
+    CK(cudaMemcpyAsync(&kept, &st->kept, sizeof(kept), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (kept > (unsigned long long)kSelTile) return LICHEE_OK;       // massive ties: not usable
+    m = (long long)kept;
+    used = true;
     return LICHEE_OK;
 }
 
@@ -1161,7 +1270,10 @@ int run_search(lichee_search *h) {
                 CK(cudaGetLastError());
                 st.num_launches++;
                 int src = 0;
-                if (run_tournament(h, m, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                bool radix = false;
+                if (m > kSelTile && run_radix_select(h, m, radix) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (radix) src = 1;
+                else if (run_tournament(h, m, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 if (run_select(h, h->d_cands(src), m, h->level(lv), 0, nullptr, 0) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 st.kernel_bytes[LICHEE_K_SELECT] += (long long)sizeof(Cand) * (long long)h->h_meta->n_cand;
             } else {
@@ -1257,6 +1369,7 @@ int lichee_search_destroy(lichee_search *h) {
     for (DevBuf &b : h->b_level) give_back(h, b);
     give_back(h, h->b_mask); give_back(h, h->b_cnt); give_back(h, h->b_off); give_back(h, h->b_tile);
     give_back(h, h->b_small);
+    give_back(h, h->b_radix);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     if (h->stream) {
         DevCtx c;
