@@ -109,6 +109,16 @@ int lichee_search_create(lichee_search **out, int32_t n_nodes, int32_t n_samples
 /* getLineageTrees() + evaluateLineageTrees(): enumerate, check, score, rank.  Blocking. */
 int lichee_search_run(lichee_search *h);
 
+/* Dynamic work stealing: search slice `slice` of `n_slices` contiguous slices of the canonical order
+ * (overrides part_rank/part_count).  With keep_ranked != 0 the ranked list, its threshold and the
+ * statistics of the earlier slices on this handle are kept, so a GPU can claim slice after slice
+ * from a counter shared by all ranks (lichee_b200/dist.py does it with the torch.distributed store).
+ * Ties rank by (slice, seq), i.e. the same canonical order as one whole search; MAX_NUM_TREES
+ * applies per slice. */
+int lichee_search_run_slice(lichee_search *h, int32_t slice, int32_t n_slices, int32_t keep_ranked);
+/* Empty ranked list and zero statistics (a rank that claimed no slice still takes part in the merge). */
+int lichee_search_clear(lichee_search *h);
+
 int lichee_search_get_stats(const lichee_search *h, lichee_search_stats *out);
 
 /* Ranked tree k (0 = lowest error score), k < stats.num_saved.

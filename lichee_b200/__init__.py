@@ -21,7 +21,8 @@ STATUS_TREE_CAP = 1
 STATUS_GROW_CAP = 2
 
 EXPORTED_SYMBOLS = [
-    "lichee_default_params", "lichee_search_create", "lichee_search_run", "lichee_search_get_stats",
+    "lichee_default_params", "lichee_search_create", "lichee_search_run", "lichee_search_run_slice",
+    "lichee_search_clear", "lichee_search_get_stats",
     "lichee_search_get_tree", "lichee_search_get_trees", "lichee_record_bytes", "lichee_search_export_ranked",
     "lichee_search_merge_ranked", "lichee_search_get_order", "lichee_search_destroy",
     "lichee_get_lineage_trees", "lichee_last_error", "lichee_version", "lichee_device_count",
@@ -79,6 +80,8 @@ def lib():
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.POINTER(SearchParams)]
         L.lichee_search_run.argtypes = [ctypes.c_void_p]
+        L.lichee_search_run_slice.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+        L.lichee_search_clear.argtypes = [ctypes.c_void_p]
         L.lichee_search_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(SearchStats)]
         L.lichee_search_get_tree.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]
@@ -183,6 +186,24 @@ class LineageSearch:
     def run(self):
         _ck(lib().lichee_search_run(self._h))
         return self.stats()
+
+    def run_slice(self, slice_id, n_slices, keep_ranked=False):
+        _ck(lib().lichee_search_run_slice(self._h, slice_id, n_slices, 1 if keep_ranked else 0))
+        return self.stats()
+
+    def run_claimed(self, n_slices, claim):
+        """Dynamic work stealing: `claim()` returns the next unclaimed slice id (or >= n_slices when
+        none is left); this GPU keeps one ranked list across everything it claims."""
+        first = True
+        while True:
+            t = int(claim())
+            if t >= n_slices:
+                break
+            self.run_slice(t, n_slices, keep_ranked=not first)
+            first = False
+        if first:                       # nothing claimed: an empty ranked list that can still be exported
+            _ck(lib().lichee_search_clear(self._h))
+        return not first
 
     def stats(self):
         st = SearchStats()

@@ -1146,16 +1146,35 @@ int harvest_events(lichee_search *h, int set) {
     return LICHEE_OK;
 }
 
+// Searches slice R of P of the canonical order.  keep = continue an earlier run_search on this handle:
+// the ranked list, its threshold and the statistics carry over (dynamic work stealing: a rank claims
+// slice after slice from a shared counter).
 template <int SPL>
-int run_search(lichee_search *h) {
+int run_search(lichee_search *h, int R, int P, bool keep) {
     const int L = h->L;
     lichee_search_stats &st = h->stats;
+    const lichee_search_stats before = st;
     st = lichee_search_stats{};
     st.num_grow_calls = 1;
-    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
-    h->flip = 0;
+    if (!keep) {
+        init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
+        h->flip = 0;
+    }
     for (int lv = 0; lv < L; lv++) h->head[lv] = h->tail[lv] = 0;
-    if (h->no_trees || L == 0) return fetch_top(h);
+    auto finish = [&]() {
+        if (keep) {                       // statistics accumulate over the slices of one search
+            st.num_trees += before.num_trees; st.num_grow_calls += before.num_grow_calls - 1;
+            st.num_checks += before.num_checks; st.num_scored += before.num_scored;
+            st.num_launches += before.num_launches; st.frontier_bytes += before.frontier_bytes;
+            st.kernel_ms_total += before.kernel_ms_total; st.status |= before.status;
+            for (int i = 0; i < LICHEE_NUM_KERNELS; i++) {
+                st.kernel_ms[i] += before.kernel_ms[i]; st.kernel_launches[i] += before.kernel_launches[i];
+                st.kernel_bytes[i] += before.kernel_bytes[i];
+            }
+        }
+        return fetch_top(h);
+    };
+    if (h->no_trees || L == 0) return finish();
 
     if (ensure(h, h->b_level[0], (size_t)h->stride) != LICHEE_OK) return LICHEE_ERR_CUDA;
     CK(cudaMemsetAsync(h->level(0), 0xff, h->stride, h->stream));
@@ -1169,7 +1188,7 @@ int run_search(lichee_search *h) {
     std::vector<bool> seen(L, false);
     for (int lv = 0; lv < L; lv++) fan[lv] = (double)h->cands[lv].size();
     long long seq_base = 0;
-    const int P = std::max(1, h->prm.part_count), R = h->prm.part_rank;
+    P = std::max(1, P);
     bool sliced = P <= 1;
     float ms = 0;
     int es = 0;
@@ -1332,7 +1351,7 @@ int run_search(lichee_search *h) {
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     st.kernel_ms_total = ms;
     st.num_trees = std::min(seq_base, (long long)h->prm.max_num_trees);
-    return fetch_top(h);
+    return finish();
 }
 
 }  // namespace
@@ -1576,7 +1595,31 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
 int lichee_search_run(lichee_search *h) {
     if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
-    const int rc = h->SP == 32 ? run_search<1>(h) : run_search<2>(h);
+    const int rc = h->SP == 32 ? run_search<1>(h, h->prm.part_rank, h->prm.part_count, false)
+                               : run_search<2>(h, h->prm.part_rank, h->prm.part_count, false);
+    if (rc == LICHEE_OK) h->ran = true;
+    return rc;
+}
+
+int lichee_search_run_slice(lichee_search *h, int32_t slice, int32_t n_slices, int32_t keep_ranked) {
+    if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
+    if (n_slices < 1 || slice < 0 || slice >= n_slices) { set_err("slice %d of %d out of range", slice, n_slices); return LICHEE_ERR_INVALID; }
+    if (keep_ranked && !h->ran) { set_err("keep_ranked needs an earlier run on this handle"); return LICHEE_ERR_STATE; }
+    CK(cudaSetDevice(h->device));
+    const int rc = h->SP == 32 ? run_search<1>(h, slice, n_slices, keep_ranked != 0) : run_search<2>(h, slice, n_slices, keep_ranked != 0);
+    if (rc == LICHEE_OK) h->ran = true;
+    return rc;
+}
+
+int lichee_search_clear(lichee_search *h) {
+    if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
+    CK(cudaGetLastError());
+    h->flip = 0;
+    h->stats = lichee_search_stats{};
+    h->stats.num_grow_calls = 0;
+    const int rc = fetch_top(h);
     if (rc == LICHEE_OK) h->ran = true;
     return rc;
 }

@@ -26,3 +26,13 @@ def allgather_ranked(search, group=None, device=None):
     out = torch.cat(parts).numpy()
     search.merge_ranked(out, world, device_ptr=False)
     return out
+
+
+def run_work_stealing(search, store, n_slices, key="lichee_b200/next_slice", group=None, device=None):
+    """One sharded search with dynamic load balance: the canonical order is cut into `n_slices`
+    contiguous slices (several per GPU) and every rank claims the next unclaimed one with an atomic
+    add on the torch.distributed store until none is left, keeping ONE ranked list (and threshold)
+    on its GPU; then the lists are merged with one all_gather.  `store` is the c10d store of the
+    process group (TCPStore / FileStore: `add` is an atomic fetch-and-add across ranks)."""
+    search.run_claimed(n_slices, lambda: store.add(key, 1) - 1)
+    return allgather_ranked(search, group=group, device=device)

@@ -88,3 +88,45 @@ def test_slices_partition_the_frontier():
             cuts = [(w * r // P, w * (r + 1) // P) for r in range(P)]
             assert cuts[0][0] == 0 and cuts[-1][1] == w
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(P - 1))
+
+
+class FakeClaimSearch(FakeSearch):
+    def __init__(self, rank):
+        super().__init__(rank)
+        self.claimed = []
+
+    def run_claimed(self, n_slices, claim):
+        while True:
+            t = claim()
+            if t >= n_slices:
+                break
+            self.claimed.append(t)
+        return bool(self.claimed)
+
+
+def _steal_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lichee_b200.dist import run_work_stealing
+    store = dist.distributed_c10d._get_default_store()
+    s = FakeClaimSearch(rank)
+    run_work_stealing(s, store, n_slices=37)
+    q.put((rank, s.claimed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_work_stealing_claims_every_slice_exactly_once_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_steal_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    claimed = sorted(t for _, c in got for t in c)
+    assert claimed == list(range(37))

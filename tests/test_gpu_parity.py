@@ -232,3 +232,36 @@ def test_published_reference_trees_on_gpu(built):
         # treeNodes / treeEdges reconstruction is consistent
         assert trees[0].treeNodes[0] == 0 and sorted(trees[0].treeNodes) == list(range(len(par)))
         assert all(par[c] == q for q, ch in trees[0].treeEdges.items() for c in ch)
+
+
+def test_work_stealing_slices_give_the_whole_search(built):
+    """Slices claimed one after another on one handle (ranked list and threshold kept), and the same
+    slices dealt to two handles out of order and merged: both equal the single whole search."""
+    import lichee_b200
+    net, prm = make_instance(11, 5, seed=4)
+    whole, trees, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 40, max_num_trees=10**9)
+    T = 12
+    s = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
+    todo = iter(range(T + 1))
+    assert s.run_claimed(T, lambda: next(todo))
+    st = s.stats()
+    assert st.num_trees == whole["num_trees"] and st.num_scored == whole["num_trees"]
+    got = s.trees()
+    assert [t.parent for t in got] == [t.parent for t in trees]
+    assert [t.errorScore for t in got] == [t.errorScore for t in trees]
+    s.close()
+    a = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
+    b = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
+    c = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
+    order_a, order_b = iter([11, 0, 5, 7, 2, T]), iter([3, 10, 1, 9, 8, 6, 4, T])
+    a.run_claimed(T, lambda: next(order_a))
+    b.run_claimed(T, lambda: next(order_b))
+    assert not c.run_claimed(T, lambda: T)                  # a rank that found nothing left to claim
+    assert a.stats().num_trees + b.stats().num_trees == whole["num_trees"] and c.stats().num_trees == 0
+    recs = np.concatenate([a.export_ranked(), b.export_ranked(), c.export_ranked()])
+    for h in (a, b, c):
+        h.merge_ranked(recs, 3)
+        m = h.trees()
+        assert [t.parent for t in m] == [t.parent for t in trees]
+        assert [t.errorScore for t in m] == [t.errorScore for t in trees]
+        h.close()
