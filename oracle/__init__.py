@@ -91,3 +91,16 @@ def canonical_search(adj, vaf, margin, top_s=1, max_trees=100000):
     m = int(min(stats[0], top_s))
     return dict(scores=sc[:m], parents=par[:m], seq=seq[:m], n_trees=int(stats[0]), n_grow=int(stats[1]),
                 n_checks=int(stats[2]), sigma=sigma[:n - 1])
+
+
+def canonical_eval_tree(vaf, margin, parent):
+    """(valid, score) of one tree under the canonical summation order (see lichee_oracle.c)."""
+    lib = _load()
+    vaf = np.ascontiguousarray(vaf, dtype=np.float64)
+    n, S = vaf.shape
+    par = np.ascontiguousarray(parent, dtype=np.int32)
+    sc = ctypes.c_double(0.0)
+    lib.lichee_canonical_eval_tree.restype = ctypes.c_int
+    ok = lib.lichee_canonical_eval_tree(ctypes.c_int(n), ctypes.c_int(S), ctypes.c_void_p(vaf.ctypes.data),
+                                        ctypes.c_double(margin), ctypes.c_void_p(par.ctypes.data), ctypes.byref(sc))
+    return bool(ok), sc.value

@@ -429,3 +429,40 @@ int lichee_canonical_search(int n, int S, const int *adj_off, const int *adj_idx
     free(c.k_score); free(c.k_seq); free(c.k_par);
     return 0;
 }
+
+/* Evaluates ONE tree given as a parent vector (TEST INFRASTRUCTURE): returns 1 if every parent
+ * satisfies the sum rule (PHYTree.checkConstraint with the children in canonical sigma order) and
+ * stores the canonical error score; used to re-verify trees returned by searches that are too large
+ * to enumerate on the CPU. */
+int lichee_canonical_eval_tree(int n, int S, const double *vaf, double margin, const int *parent, double *score_out) {
+    canon_t c; memset(&c, 0, sizeof(c));
+    c.n = n; c.S = S; c.L = n - 1; c.vaf = vaf; c.margin = margin;
+    c.sigma = (int *)malloc(sizeof(int) * (n + 1));
+    c.ch = (int **)malloc(sizeof(int *) * n); c.nch = (int *)calloc(n, sizeof(int));
+    double *mass = (double *)calloc(n, sizeof(double));
+    for (int v = 0; v < n; v++) { c.ch[v] = (int *)malloc(sizeof(int) * (n + 1)); for (int s = 0; s < S; s++) mass[v] += vaf[(size_t)v * S + s]; }
+    for (int t = 0; t < c.L; t++) c.sigma[t] = t + 1;
+    for (int i = 1; i < c.L; i++) {
+        int x = c.sigma[i], j = i;
+        while (j > 0 && mass[c.sigma[j - 1]] < mass[x]) { c.sigma[j] = c.sigma[j - 1]; j--; }
+        c.sigma[j] = x;
+    }
+    int ok = 1;
+    for (int t = 0; t < c.L; t++) {
+        int v = c.sigma[t], p = parent[v];
+        if (p < 0 || p >= n || p == v) { ok = 0; break; }
+        c.ch[p][c.nch[p]++] = v;
+    }
+    for (int p = 0; p < n && ok; p++) {
+        if (c.nch[p] == 0) continue;
+        for (int s = 0; s < S && ok; s++) {
+            double sum = 0;
+            for (int k = 0; k < c.nch[p]; k++) sum += vaf[(size_t)c.ch[p][k] * S + s];
+            if (sum > vaf[(size_t)p * S + s] + margin) ok = 0;
+        }
+    }
+    if (ok && score_out) *score_out = canon_score(&c);
+    for (int v = 0; v < n; v++) free(c.ch[v]);
+    free(c.sigma); free(c.ch); free(c.nch); free(mass);
+    return ok;
+}

@@ -265,3 +265,48 @@ def test_work_stealing_slices_give_the_whole_search(built):
         assert [t.parent for t in m] == [t.parent for t in trees]
         assert [t.errorScore for t in m] == [t.errorScore for t in trees]
         h.close()
+
+
+@pytest.mark.parametrize("n_clusters,n_samples,cap", [(40, 20, 1 << 22), (120, 64, 1 << 22)])
+def test_full_size_properties(built, n_clusters, n_samples, cap):
+    """BASELINE configs[3] and [4] at a tree count the CPU cannot enumerate: properties that do not
+    depend on size.  Every returned tree is a spanning tree that passes the sum rule and carries
+    exactly the score the CPU evaluator computes for it; the list is ranked by (score, seq); the
+    answer does not move with the frontier capacity (chunking), with a re-run on the same handle, or
+    with the choice of slices; and a prefix cap only ever removes trees (seq < cap)."""
+    import lichee_b200
+    net, prm = make_instance(n_clusters, n_samples, seed=2026)
+    vaf = np.array(net.aaf)
+    s = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap)
+    st = s.run()
+    trees = s.trees()
+    assert st.num_trees == cap and st.num_scored == cap and (st.status & 1)
+    assert len(trees) == 1000
+    edges = {(p, c) for p, ch in enumerate(net.adj) for c in ch}
+    for t in trees:
+        assert all((t.parent[v], v) in edges for v in range(1, net.n))       # uses network edges only
+        assert sorted(t.treeNodes) == list(range(net.n))                      # spans every node
+        ok, sc = oracle.canonical_eval_tree(vaf, prm.vaf_error_margin, t.parent)
+        assert ok and sc == t.errorScore                                      # valid, bit-equal score
+        assert 0 <= t.seq < cap
+    keys = [(t.errorScore, t.seq) for t in trees]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    again = s.run()
+    assert again.num_trees == st.num_trees and [t.parent for t in s.trees()] == [t.parent for t in trees]   # idempotent
+    s.close()
+    small = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap,
+                                      level_capacity=1 << 16)
+    st2 = small.run()
+    t2 = small.trees()
+    assert st2.num_trees == cap and st2.num_launches > st.num_launches
+    assert [(t.errorScore, t.seq, t.parent) for t in t2] == [(t.errorScore, t.seq, t.parent) for t in trees]
+    small.close()
+    # a tighter prefix cap keeps exactly the trees of the longer run whose seq is below it
+    half = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap // 4)
+    half.run()
+    th = half.trees()
+    best_possible = sorted((t.errorScore, t.seq) for t in trees if t.seq < cap // 4)
+    assert all(t.seq < cap // 4 for t in th)
+    kept = {(t.errorScore, t.seq) for t in th}
+    assert set(best_possible) <= kept
+    half.close()
