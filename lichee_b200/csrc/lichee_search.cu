@@ -121,6 +121,20 @@ __device__ __forceinline__ void stage_network(const DevNet &net, int level, doub
     __syncthreads();
 }
 
+// Row q of the centroid matrix for this lane: samples `lane` and `lane+32`.  With two samples per lane
+// the halves are interleaved in shared memory ({x[l], x[l+32]} adjacent) so one 128-bit load gets both.
+template <int SPL>
+__device__ __forceinline__ void load_row(const double *vaf_s, int q, int SP, int lane, double &x0, double &x1) {
+    if (SPL == 2) {
+        const double2 v = reinterpret_cast<const double2 *>(vaf_s)[q * 32 + lane];
+        x0 = v.x;
+        x1 = v.y;
+    } else {
+        x0 = vaf_s[q * SP + lane];
+        x1 = 0.0;
+    }
+}
+
 // Sum of the centroid rows of the children of parent q inside item word-vector w, in ascending tree
 // position: the canonical accumulation order.  rmax = highest byte lane that can hold an
 // assigned position.  Returns the sums for samples lane and lane+32.
@@ -130,13 +144,17 @@ __device__ __forceinline__ void child_sums(unsigned w, unsigned q, int rmax, int
     const unsigned m = __vcmpeq4(w, q * 0x01010101u);
     s0 = 0.0;
     s1 = 0.0;
-    for (int r = 0; r <= rmax; r++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        if (r > rmax) break;
         unsigned kids = __ballot_sync(kFull, (m >> (8 * r)) & 1u);
         while (kids) {
             const int row = r * W + __ffs(kids);             // position + 1 = row of the child
             kids &= kids - 1;
-            s0 = __dadd_rn(s0, vaf_s[row * SP + lane]);
-            if (SPL == 2) s1 = __dadd_rn(s1, vaf_s[row * SP + 32 + lane]);
+            double x0, x1;
+            load_row<SPL>(vaf_s, row, SP, lane, x0, x1);
+            s0 = __dadd_rn(s0, x0);
+            if (SPL == 2) s1 = __dadd_rn(s1, x1);
         }
     }
 }
@@ -165,7 +183,7 @@ __device__ __forceinline__ void parent_presence(unsigned w, int rmax, unsigned p
 // Output: 128-bit pass mask + pass count per item.
 // ------------------------------------------------------------------------------------------
 template <int SPL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long n_items,
              uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -179,8 +197,8 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
     const uint4 sok4 = net.static_ok[level];
     const unsigned sok[4] = {sok4.x, sok4.y, sok4.z, sok4.w};
     const int rmax = level > 0 ? (level - 1) / (net.stride >> 2) : -1;
-    const double xv0 = vaf_s[(level + 1) * SP + lane];
-    const double xv1 = SPL == 2 ? vaf_s[(level + 1) * SP + 32 + lane] : 0.0;
+    double xv0, xv1;
+    load_row<SPL>(vaf_s, level + 1, SP, lane, xv0, xv1);
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const int wstride = net.stride >> 2;
@@ -203,11 +221,13 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
                 if ((pw >> (q & 31)) & 1u) {
                     double s0, s1;
                     child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
+                    double a0, a1;
+                    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
                     s0 = __dadd_rn(s0, xv0);
-                    bool bad = valid0 && s0 > __dadd_rn(vaf_s[q * SP + lane], net.margin);
+                    bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
                     if (SPL == 2) {
                         s1 = __dadd_rn(s1, xv1);
-                        bad |= valid1 && s1 > __dadd_rn(vaf_s[q * SP + 32 + lane], net.margin);
+                        bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
                     }
                     pass = !__any_sync(kFull, bad);
                 } else {
@@ -414,7 +434,7 @@ __device__ __forceinline__ double parent_excess(double s0, double s1, double a0,
 // and appends the trees that beat the threshold with a provisional sequence number; seq_fixup_kernel
 // turns that into the canonical one once the scan has run.
 template <int SPL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, long long item_base,
             uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out, int part, TopMeta *meta,
             int num_save, Cand *__restrict__ cands, long long cand_cap) {
@@ -447,8 +467,8 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const int wstride = net.stride >> 2;
     const int rmax = level > 0 ? (level - 1) / wstride : -1;
-    const double xv0 = vaf_s[(level + 1) * SP + lane];
-    const double xv1 = SPL == 2 ? vaf_s[(level + 1) * SP + 32 + lane] : 0.0;
+    double xv0, xv1;
+    load_row<SPL>(vaf_s, level + 1, SP, lane, xv0, xv1);
     const double tau = meta->tau;
     const bool full = meta->count >= (unsigned)num_save;
     // a tree can only enter the full list with sqrt(total) < tau; totals clearly above tau^2 skip the sqrt
@@ -479,7 +499,8 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 const unsigned q = g * 32 + bq;
                 double s0, s1;
                 child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
-                const double a0 = vaf_s[q * SP + lane], a1 = SPL == 2 ? vaf_s[q * SP + 32 + lane] : 0.0;
+                double a0, a1;
+                load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
                 const double Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
                 if (lane == bq) E[g] = Eq;
                 if ((candq[g] >> bq) & 1u) {
@@ -1499,7 +1520,10 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     std::vector<int> qof(n, 0);
     for (int t = 0; t < h->L; t++) qof[h->sigma[t]] = t + 1;
     std::vector<double> vp((size_t)n * h->SP, 0.0);
-    for (int v = 0; v < n; v++) for (int s = 0; s < S; s++) vp[(size_t)qof[v] * h->SP + s] = vaf[(size_t)v * S + s];
+    // SP == 64: the two halves of a row are interleaved ({x[l], x[l+32]} adjacent) for 128-bit loads
+    for (int v = 0; v < n; v++)
+        for (int s = 0; s < S; s++)
+            vp[(size_t)qof[v] * h->SP + (h->SP == 64 ? 2 * (s & 31) + (s >> 5) : s)] = vaf[(size_t)v * S + s];
     std::vector<uint8_t> cd((size_t)Lp * kMaxN, 0), nc(kMaxN, 0);
     std::vector<uint4> sok(Lp, make_uint4(0, 0, 0, 0));
     for (int t = 0; t < h->L; t++) {
