@@ -42,6 +42,7 @@ namespace {
 constexpr int kWarpsPerBlock = 16;                 // 512 threads share one copy of the matrix
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxN = LICHEE_MAX_NODES;
+constexpr int kMaxIncremental = 12;                // more changed parent rows than this: recompute the item
 constexpr int kSelThreads = 1024;
 constexpr int kSelTile = 1024;
 constexpr unsigned kFull = 0xffffffffu;
@@ -434,10 +435,10 @@ __device__ __forceinline__ double parent_excess(double s0, double s1, double a0,
 // and appends the trees that beat the threshold with a provisional sequence number; seq_fixup_kernel
 // turns that into the canonical one once the scan has run.
 template <int SPL>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 2)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, long long item_base,
             uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out, int part, TopMeta *meta,
-            int num_save, Cand *__restrict__ cands, long long cand_cap) {
+            int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
@@ -477,45 +478,82 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     unsigned long long my_valid = 0;
 
-    for (long long it = warp0; it < n_items; it += nwarps) {
+    // A warp walks a contiguous run of items.  Neighbours in the canonical order differ in very few
+    // parent bytes (usually one), so after the first item of a run only the rows of the parents that
+    // gained or lost a child are recomputed; every other E, E' and pass bit carries over unchanged.
+    // Rows: E[q] = excess of parent q without the last node, F[q] = with it (passing candidates).
+    // Lane l keeps rows l, l+32, l+64, l+96.  passq = passing candidates by row.
+    double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned passq[4] = {0, 0, 0, 0};
+    unsigned w_prev = 0;
+    for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len)
+    for (long long it = run0; it < run0 + run_len && it < n_items; it++) {
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
         unsigned um[4];
         parent_presence(w, rmax, um);
-        // Rows: E[q] = excess of parent q without the last node, F[q] = with it (passing candidates).
-        // Lane l keeps rows l, l+32, l+64, l+96.  passq = passing candidates by row.
-        double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
-        unsigned passq[4];
+        unsigned todo[4];                                    // rows to (re)compute for this item
+        bool fresh = it == run0;
+        if (!fresh) {
+            // rows named by a byte that changed, in the old or the new item
+            unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            const unsigned diff = w ^ w_prev;
+            for (int r = 0; r <= rmax; r++) {
+                if ((diff >> (8 * r)) & 0xffu) {
+                    const unsigned bo = (w_prev >> (8 * r)) & 0xffu, bn = (w >> (8 * r)) & 0xffu;
+                    const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
+                    c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
+                    c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
+                    c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
+                    c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+                }
+            }
+            todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
+            todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
+            if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
+        }
+        w_prev = w;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            // candidates with no child in this item: everything about them is static
-            const unsigned absent = candq[g] & ~um[g] & okq[g];
-            passq[g] = absent;
-            if ((absent >> lane) & 1u) F[g] = fstat_s[g * 32 + lane];
-            // parents present in the item
-            unsigned rows = um[g];
+            unsigned rows;
+            if (fresh) {
+                // candidates with no child in this item: everything about them is static
+                const unsigned absent = candq[g] & ~um[g] & okq[g];
+                passq[g] = absent;
+                E[g] = 0.0;
+                F[g] = ((absent >> lane) & 1u) ? fstat_s[g * 32 + lane] : 0.0;
+                rows = um[g];
+            } else {
+                rows = todo[g];
+            }
             while (rows) {
                 const int bq = __ffs(rows) - 1;
                 rows &= rows - 1;
                 const unsigned q = g * 32 + bq;
-                double s0, s1;
-                child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
-                double a0, a1;
-                load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
-                const double Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
-                if (lane == bq) E[g] = Eq;
-                if ((candq[g] >> bq) & 1u) {
-                    s0 = __dadd_rn(s0, xv0);
-                    bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
-                    if (SPL == 2) {
-                        s1 = __dadd_rn(s1, xv1);
-                        bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
+                double Eq = 0.0, Fq = 0.0;
+                bool pass = false;
+                if ((um[g] >> bq) & 1u) {                   // parent present in the item
+                    double s0, s1, a0, a1;
+                    child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
+                    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
+                    Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                    if ((candq[g] >> bq) & 1u) {
+                        s0 = __dadd_rn(s0, xv0);
+                        bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
+                        if (SPL == 2) {
+                            s1 = __dadd_rn(s1, xv1);
+                            bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
+                        }
+                        if (!__any_sync(kFull, bad)) {
+                            Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+                            pass = true;
+                        }
                     }
-                    if (!__any_sync(kFull, bad)) {
-                        const double Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
-                        if (lane == bq) F[g] = Fq;
-                        passq[g] |= 1u << bq;
-                    }
+                } else if (((candq[g] & okq[g]) >> bq) & 1u) {          // childless candidate: static
+                    Fq = fstat_s[q];
+                    pass = true;
                 }
+                if (lane == bq) { E[g] = Eq; F[g] = Fq; }
+                passq[g] = pass ? passq[g] | (1u << bq) : passq[g] & ~(1u << bq);
             }
         }
         // pass mask by candidate index (canonical order of the trees of this item)
@@ -991,6 +1029,7 @@ struct lichee_search {
     std::vector<DevBuf> b_level;             // frontier buffers, grown on demand
     std::vector<long long> head, tail;
     long long cap = 0;                       // upper bound on items per level buffer
+    long long cand_cap = 0;                  // upper bound on candidates one last-level launch may append
     DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_cands[2], b_top[2], b_tree[2];
     ScanOut *h_scan = nullptr;               // pinned
     TopMeta *h_meta = nullptr;               // pinned
@@ -1255,7 +1294,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             B = std::min(B, std::max(1024ll, guess));
         } else {
             // every passing choice of the last node may become a candidate: keep them all
-            B = std::min(B, std::max(1ll, std::min(h->cap, leaf_ramp) / std::max(1ll, kcand)));
+            B = std::min(B, std::max(1ll, std::min(h->cand_cap, leaf_ramp) / std::max(1ll, kcand)));
         }
         if (B < 1) B = 1;
         const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
@@ -1275,9 +1314,13 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         } else {
             // last level: check and scoring fused
             if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
-            leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem_leaf, h->stream>>>(
+            // contiguous runs of items per warp (incremental evaluation): long enough to amortise the
+            // first full item, short enough to keep every warp slot of the grid busy
+            const int grid = grid_for(B);
+            int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
+            leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, B, h->head[lv], h->d_mask(), h->d_cnt(), R, h->d_meta(), h->prm.num_save,
-                h->d_cands(0), cand_cap);
+                h->d_cands(0), cand_cap, run_len);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_LEAF]++;
             st.kernel_bytes[LICHEE_K_LEAF] += B * (long long)(h->stride + 20);
@@ -1322,7 +1365,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             CK(cudaEventRecord(h->evk[es][4], h->stream));
             h->evn[es] = 5;
             // widen the next leaf launch once the threshold rejects most trees
-            if ((long long)h->h_meta->n_cand * 8 < leaf_ramp) leaf_ramp = std::min(leaf_ramp * 4, h->cap);
+            if ((long long)h->h_meta->n_cand * 8 < leaf_ramp) leaf_ramp = std::min(leaf_ramp * 4, h->cand_cap);
             const long long total = leaf_total;
             st.num_checks += B * kcand;
             st.num_grow_calls += total;
@@ -1581,6 +1624,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
     h->chunk_max = std::min<long long>(h->cap, 1ll << 20);
+    h->cand_cap = std::max<long long>(h->cap, 1ll << 23);
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
     CKE(ensure(h, h->b_small, 256));
