@@ -484,13 +484,11 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     // Rows: E[q] = excess of parent q without the last node, F[q] = with it (passing candidates).
     // Lane l keeps rows l, l+32, l+64, l+96.  passq = passing candidates by row.
     double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
-    unsigned passq[4] = {0, 0, 0, 0};
+    unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};   // pb: pass bits by candidate index
     unsigned w_prev = 0;
     for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len)
     for (long long it = run0; it < run0 + run_len && it < n_items; it++) {
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
-        unsigned um[4];
-        parent_presence(w, rmax, um);
         unsigned todo[4];                                    // rows to (re)compute for this item
         bool fresh = it == run0;
         if (!fresh) {
@@ -512,6 +510,10 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
         }
         w_prev = w;
+        if (fresh) {
+            parent_presence(w, rmax, um);
+            pb[0] = pb[1] = pb[2] = pb[3] = 0;
+        }
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             unsigned rows;
@@ -531,6 +533,10 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 const unsigned q = g * 32 + bq;
                 double Eq = 0.0, Fq = 0.0;
                 bool pass = false;
+                if (!fresh) {                                // presence of a changed row: any byte equal to q
+                    const bool here = __ballot_sync(kFull, __vcmpeq4(w, q * 0x01010101u) != 0) != 0;
+                    um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
+                }
                 if ((um[g] >> bq) & 1u) {                   // parent present in the item
                     double s0, s1, a0, a1;
                     child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
@@ -554,15 +560,25 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 }
                 if (lane == bq) { E[g] = Eq; F[g] = Fq; }
                 passq[g] = pass ? passq[g] | (1u << bq) : passq[g] & ~(1u << bq);
+                if ((candq[g] >> bq) & 1u) {                 // same bit in the mask by candidate index
+                    const unsigned i = cidx_s[q], bit = 1u << (i & 31);
+                    pb[0] = (i >> 5) == 0 ? (pass ? pb[0] | bit : pb[0] & ~bit) : pb[0];
+                    pb[1] = (i >> 5) == 1 ? (pass ? pb[1] | bit : pb[1] & ~bit) : pb[1];
+                    pb[2] = (i >> 5) == 2 ? (pass ? pb[2] | bit : pb[2] & ~bit) : pb[2];
+                    pb[3] = (i >> 5) == 3 ? (pass ? pb[3] | bit : pb[3] & ~bit) : pb[3];
+                }
             }
         }
-        // pass mask by candidate index (canonical order of the trees of this item)
-        unsigned pb[4] = {0, 0, 0, 0};
+        // pass mask by candidate index (canonical order of the trees of this item): rows handled in the
+        // loop above set their bit there; the static childless candidates of a fresh item are added here
+        if (fresh) {
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const unsigned i = ((passq[g] >> lane) & 1u) ? cidx_s[g * 32 + lane] : 0xffu;
+            for (int g = 0; g < 4; g++) {
+                const unsigned absent = candq[g] & ~um[g] & okq[g];
+                const unsigned i = ((absent >> lane) & 1u) ? cidx_s[g * 32 + lane] : 0xffu;
 #pragma unroll
-            for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
+                for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
+            }
         }
         {
             const unsigned cnt = __popc(pb[0]) + __popc(pb[1]) + __popc(pb[2]) + __popc(pb[3]);
@@ -596,13 +612,14 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             double x = A;
 #pragma unroll
             for (int st = 0; st < 5; st++) x = __dadd_rn(x, rcv[st]);
-            unsigned b = passq[g];
+            // lane l now holds the total of the tree that hangs the last node under row g*32+l: every
+            // tree of the item is evaluated at once, and only the few that may beat the threshold
+            // go through the square root and the append
+            unsigned b = __ballot_sync(kFull, ((passq[g] >> lane) & 1u) && !(x > tau2_hi));
             while (b) {
                 const int bq = __ffs(b) - 1;
                 b &= b - 1;
-                const double total = __shfl_sync(kFull, x, bq);
-                if (total > tau2_hi) continue;
-                const double score = __dsqrt_rn(total);
+                const double score = __dsqrt_rn(__shfl_sync(kFull, x, bq));
                 if (!full || score < tau) {
                     if (lane == 0) {
                         const unsigned long long slot = atomicAdd(&meta->n_cand, 1ull);
