@@ -472,8 +472,17 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     load_row<SPL>(vaf_s, level + 1, SP, lane, xv0, xv1);
     const double tau = meta->tau;
     const bool full = meta->count >= (unsigned)num_save;
-    // a tree can only enter the full list with sqrt(total) < tau; totals clearly above tau^2 skip the sqrt
-    const double tau2_hi = full ? __dmul_rn(__dmul_rn(tau, tau), 1.0 + 1e-12) : INFINITY;
+    // A tree enters a full list only with sqrt_rn(total) < tau.  sqrt_rn is monotone, so that is
+    // total <= tmax with tmax = the largest double whose rounded square root is below tau: found
+    // once per thread by stepping a few ulps around tau*tau.  No square root for rejected trees.
+    double tmax = INFINITY;
+    if (full) {
+        double t = __dmul_rn(tau, tau);
+        for (int i = 0; i < 8 && t > 0.0 && __dsqrt_rn(t) >= tau; i++) t = __longlong_as_double(__double_as_longlong(t) - 1);
+        for (int i = 0; i < 8 && __dsqrt_rn(__longlong_as_double(__double_as_longlong(t) + 1)) < tau; i++)
+            t = __longlong_as_double(__double_as_longlong(t) + 1);
+        tmax = __dsqrt_rn(t) < tau ? t : -1.0;             // tau == 0: nothing can beat it
+    }
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     unsigned long long my_valid = 0;
@@ -615,7 +624,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             // lane l now holds the total of the tree that hangs the last node under row g*32+l: every
             // tree of the item is evaluated at once, and only the few that may beat the threshold
             // go through the square root and the append
-            unsigned b = __ballot_sync(kFull, ((passq[g] >> lane) & 1u) && !(x > tau2_hi));
+            unsigned b = __ballot_sync(kFull, ((passq[g] >> lane) & 1u) && x <= tmax);
             while (b) {
                 const int bq = __ffs(b) - 1;
                 b &= b - 1;
