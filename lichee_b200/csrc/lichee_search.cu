@@ -495,9 +495,13 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};   // pb: pass bits by candidate index
     unsigned w_prev = 0;
-    for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len)
-    for (long long it = run0; it < run0 + run_len && it < n_items; it++) {
-        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+    for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len) {
+    const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
+    unsigned w_next = lane < wstride ? __ldg(items + run0 * wstride + lane) : 0xffffffffu;
+    for (long long it = run0; it < run1; it++) {
+        const unsigned w = w_next;
+        // the next item's bytes are requested now so that their latency hides behind this item's work
+        if (it + 1 < run1 && lane < wstride) w_next = __ldg(items + (it + 1) * wstride + lane);
         unsigned todo[4];                                    // rows to (re)compute for this item
         bool fresh = it == run0;
         if (!fresh) {
@@ -647,6 +651,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 }
             }
         }
+    }
     }
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
 }
@@ -1332,7 +1337,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;   // the chunk before last
         h->ev_leaf[es] = leaf;
         CK(cudaEventRecord(h->evk[es][0], h->stream));
-        const long long cand_cap = B * kcand;
+        const long long cand_cap = std::min(B * kcand, h->cand_cap);
         if (!leaf) {
             if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_launches[LICHEE_K_CHECK]++;
@@ -1343,7 +1348,11 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // contiguous runs of items per warp (incremental evaluation): long enough to amortise the
             // first full item, short enough to keep every warp slot of the grid busy
             const int grid = grid_for(B);
-            int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
+            // several runs per warp (load balance between cheap and expensive runs), each 16..64 items long
+            static const int env_runs = getenv("LICHEE_RUNS_PER_WARP") ? atoi(getenv("LICHEE_RUNS_PER_WARP")) : 1;
+            static const int env_minrun = getenv("LICHEE_MIN_RUN") ? atoi(getenv("LICHEE_MIN_RUN")) : 1;
+            int run_len = (int)std::min<long long>(64, std::max<long long>(env_minrun, B / ((long long)grid * kWarpsPerBlock * env_runs)));
+            if (run_len > B) run_len = (int)std::max<long long>(1, B);
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, B, h->head[lv], h->d_mask(), h->d_cnt(), R, h->d_meta(), h->prm.num_save,
                 h->d_cands(0), cand_cap, run_len);
@@ -1365,7 +1374,16 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // some of them beat the threshold (most chunks: none)
             CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
-            long long m = (long long)std::min<unsigned long long>(h->h_meta->n_cand, (unsigned long long)cand_cap);
+            if (h->h_meta->n_cand > (unsigned long long)cand_cap) {
+                // more survivors than the candidate buffer holds (the threshold was stale for a whole
+                // region): nothing was consumed yet, so shrink the chunk and run it again
+                reset_n_cand<<<1, 1, 0, h->stream>>>(h->d_meta());
+                st.num_launches++;
+                leaf_ramp = std::max<long long>(kcand, std::min(leaf_ramp, B * kcand) / 4);
+                h->evn[es] = 0;
+                continue;
+            }
+            long long m = (long long)h->h_meta->n_cand;
             leaf_total = (long long)h->h_meta->n_valid;
             if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
@@ -1650,7 +1668,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
     h->chunk_max = std::min<long long>(h->cap, 1ll << 20);
-    h->cand_cap = std::max<long long>(h->cap, 1ll << 23);
+    h->cand_cap = std::max<long long>(h->cap, getenv("LICHEE_CAND_CAP_LOG2") ? 1ll << atoi(getenv("LICHEE_CAND_CAP_LOG2")) : 1ll << 23);
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
     CKE(ensure(h, h->b_small, 256));
