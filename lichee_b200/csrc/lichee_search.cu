@@ -186,61 +186,120 @@ __device__ __forceinline__ void parent_presence(unsigned w, int rmax, unsigned p
 template <int SPL>
 __global__ void __launch_bounds__(kThreads, 3)
 check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long n_items,
-             uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out) {
+             uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out, int run_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    __shared__ uint8_t cidx_s[kMaxN];          // by row: candidate index (valid where candq has the bit)
+    __shared__ unsigned candq_s[4], okq_s[4];  // rows that are candidates / that pass with no other child
+    const int k = net.ncand[level];
+    if (threadIdx.x < 4) { candq_s[threadIdx.x] = 0; okq_s[threadIdx.x] = 0; }
     stage_network(net, level, vaf_s, cand_s);
+    const uint4 sok4 = net.static_ok[level];
+    const unsigned sok[4] = {sok4.x, sok4.y, sok4.z, sok4.w};
+    if (threadIdx.x < k) {
+        const unsigned q = cand_s[threadIdx.x];
+        cidx_s[q] = (uint8_t)threadIdx.x;
+        atomicOr(&candq_s[q >> 5], 1u << (q & 31));
+        const unsigned sw = (threadIdx.x >> 5) == 0 ? sok4.x : (threadIdx.x >> 5) == 1 ? sok4.y : (threadIdx.x >> 5) == 2 ? sok4.z : sok4.w;
+        if ((sw >> (threadIdx.x & 31)) & 1u) atomicOr(&okq_s[q >> 5], 1u << (q & 31));
+    }
+    __syncthreads();
+    const unsigned candq[4] = {candq_s[0], candq_s[1], candq_s[2], candq_s[3]};
+    const unsigned okq[4] = {okq_s[0], okq_s[1], okq_s[2], okq_s[3]};
 
     const int lane = threadIdx.x & 31;
     const int SP = net.SP;
-    const int k = net.ncand[level];
-    const uint4 sok4 = net.static_ok[level];
-    const unsigned sok[4] = {sok4.x, sok4.y, sok4.z, sok4.w};
-    const int rmax = level > 0 ? (level - 1) / (net.stride >> 2) : -1;
+    const int wstride = net.stride >> 2;
+    const int rmax = level > 0 ? (level - 1) / wstride : -1;
     double xv0, xv1;
     load_row<SPL>(vaf_s, level + 1, SP, lane, xv0, xv1);
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
-    const int wstride = net.stride >> 2;
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
 
-    for (long long it = warp0; it < n_items; it += nwarps) {
-        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
-        unsigned pm[4];
-        parent_presence(w, rmax, pm);
-        unsigned bits[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) {                       // static indices keep the masks in registers
-            unsigned bg = 0;
-            const int hi = k - g * 32 < 32 ? k - g * 32 : 32;
-            for (int j = 0; j < hi; j++) {
-                const unsigned q = cand_s[g * 32 + j];
-                const unsigned pw = (q >> 5) == 0 ? pm[0] : (q >> 5) == 1 ? pm[1] : (q >> 5) == 2 ? pm[2] : pm[3];
-                bool pass;
-                if ((pw >> (q & 31)) & 1u) {
-                    double s0, s1;
-                    child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
-                    double a0, a1;
-                    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
-                    s0 = __dadd_rn(s0, xv0);
-                    bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
-                    if (SPL == 2) {
-                        s1 = __dadd_rn(s1, xv1);
-                        bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
-                    }
-                    pass = !__any_sync(kFull, bad);
-                } else {
-                    pass = (sok[g] >> j) & 1u;               // no other child: decided once per network
-                }
-                if (pass) bg |= 1u << j;
-            }
-            bits[g] = bg;
+    // sum rule for candidate row q (present in the item): children + the new node against VAF(q) + margin
+    auto passes = [&](unsigned w, unsigned q) {
+        double s0, s1, a0, a1;
+        child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
+        load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
+        s0 = __dadd_rn(s0, xv0);
+        bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
+        if (SPL == 2) {
+            s1 = __dadd_rn(s1, xv1);
+            bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
         }
-        if (lane == 0) {
-            mask_out[it] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
-            count_out[it] = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
+        return !__any_sync(kFull, bad);
+    };
+
+    // Like the last-level kernel, a warp walks a contiguous run of items and, after the first one,
+    // re-decides only the candidates whose set of children changed.
+    unsigned bits[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0};
+    unsigned w_prev = 0;
+    for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len) {
+        const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
+        for (long long it = run0; it < run1; it++) {
+            const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+            bool fresh = it == run0;
+            unsigned todo[4] = {0, 0, 0, 0};
+            if (!fresh) {
+                unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                const unsigned diff = w ^ w_prev;
+                for (int r = 0; r <= rmax; r++) {
+                    if ((diff >> (8 * r)) & 0xffu) {
+                        const unsigned bo = (w_prev >> (8 * r)) & 0xffu, bn = (w >> (8 * r)) & 0xffu;
+                        const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
+                        c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
+                        c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
+                        c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
+                        c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+                    }
+                }
+                todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
+                todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
+                if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
+            }
+            w_prev = w;
+            if (fresh) {
+                parent_presence(w, rmax, um);
+#pragma unroll
+                for (int g = 0; g < 4; g++) {               // static indices keep the masks in registers
+                    unsigned bg = 0;
+                    const int hi = k - g * 32 < 32 ? k - g * 32 : 32;
+                    for (int j = 0; j < hi; j++) {
+                        const unsigned q = cand_s[g * 32 + j];
+                        const unsigned pw = (q >> 5) == 0 ? um[0] : (q >> 5) == 1 ? um[1] : (q >> 5) == 2 ? um[2] : um[3];
+                        const bool pass = ((pw >> (q & 31)) & 1u) ? passes(w, q) : ((sok[g] >> j) & 1u) != 0;
+                        if (pass) bg |= 1u << j;
+                    }
+                    bits[g] = bg;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    unsigned rows = todo[g];
+                    while (rows) {
+                        const int bq = __ffs(rows) - 1;
+                        rows &= rows - 1;
+                        const unsigned q = g * 32 + bq;
+                        const bool here = __ballot_sync(kFull, __vcmpeq4(w, q * 0x01010101u) != 0) != 0;
+                        um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
+                        if ((candq[g] >> bq) & 1u) {
+                            const bool pass = here ? passes(w, q) : ((okq[g] >> bq) & 1u) != 0;
+                            const unsigned i = cidx_s[q], bit = 1u << (i & 31);
+                            bits[0] = (i >> 5) == 0 ? (pass ? bits[0] | bit : bits[0] & ~bit) : bits[0];
+                            bits[1] = (i >> 5) == 1 ? (pass ? bits[1] | bit : bits[1] & ~bit) : bits[1];
+                            bits[2] = (i >> 5) == 2 ? (pass ? bits[2] | bit : bits[2] & ~bit) : bits[2];
+                            bits[3] = (i >> 5) == 3 ? (pass ? bits[3] | bit : bits[3] & ~bit) : bits[3];
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                mask_out[it] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+                count_out[it] = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
+            }
         }
     }
 }
@@ -1116,8 +1175,9 @@ int grid_for(long long items) {
 
 template <int SPL>
 int launch_check(lichee_search *h, int lv, const unsigned *items, long long n_items) {
-    check_kernel<SPL><<<grid_for(n_items), kThreads, h->smem, h->stream>>>(h->net, lv, items, n_items,
-                                                                          h->d_mask(), h->d_cnt());
+    const int grid = grid_for(n_items);
+    const int run_len = (int)std::min<long long>(64, std::max<long long>(1, n_items / ((long long)grid * kWarpsPerBlock)));
+    check_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(h->net, lv, items, n_items, h->d_mask(), h->d_cnt(), run_len);
     CK(cudaGetLastError());
     return LICHEE_OK;
 }
