@@ -156,6 +156,10 @@ int lichee_get_lineage_trees(int32_t n_nodes, int32_t n_samples, const int32_t *
                              const lichee_search_params *params, lichee_search_stats *stats,
                              double *scores, int32_t *parents, int32_t *orders);
 
+/* Frees the device buffers, streams and events that destroyed handles returned to the process-wide
+ * pool (live handles are not touched).  Optional: the pool is otherwise kept until process exit. */
+int lichee_release_cached_memory(void);
+
 const char *lichee_last_error(void);
 const char *lichee_version(void);
 int lichee_device_count(void);

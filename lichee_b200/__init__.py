@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "lichee_search_clear", "lichee_search_get_stats",
     "lichee_search_get_tree", "lichee_search_get_trees", "lichee_record_bytes", "lichee_search_export_ranked",
     "lichee_search_merge_ranked", "lichee_search_get_order", "lichee_search_destroy",
-    "lichee_get_lineage_trees", "lichee_last_error", "lichee_version", "lichee_device_count",
+    "lichee_get_lineage_trees", "lichee_release_cached_memory", "lichee_last_error", "lichee_version", "lichee_device_count",
 ]
 
 
@@ -99,6 +99,11 @@ def lib():
 def _ck(rc):
     if rc != 0:
         raise LicheeError(rc, lib().lichee_last_error().decode())
+
+
+def release_cached_memory():
+    """Returns the pooled device buffers / streams of destroyed searches to the driver."""
+    _ck(lib().lichee_release_cached_memory())
 
 
 def default_params():

@@ -1069,7 +1069,7 @@ struct DevicePool {
     void release(int dev) {
         std::lock_guard<std::mutex> g(mu);
         for (auto it = free_list.begin(); it != free_list.end();) {
-            if (dev < 0 || it->first.first == dev) { cudaFree(it->second); it = free_list.erase(it); } else ++it;
+            if (dev < 0 || it->first.first == dev) { cudaSetDevice(it->first.first); cudaFree(it->second); it = free_list.erase(it); } else ++it;
         }
     }
 };
@@ -1535,6 +1535,22 @@ void lichee_default_params(lichee_search_params *p) {
     p->max_num_grow_calls = 100000000;  // Parameters.MAX_NUM_GROW_CALLS
     p->part_rank = 0;
     p->part_count = 1;
+}
+
+int lichee_release_cached_memory(void) {
+    g_pool.release(-1);
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    for (auto &kv : g_ctx.free_list) {
+        DevCtx &c = kv.second;
+        cudaSetDevice(kv.first);
+        if (c.pinned) cudaFreeHost(c.pinned);
+        if (c.ev0) cudaEventDestroy(c.ev0);
+        if (c.ev1) cudaEventDestroy(c.ev1);
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) if (c.evk[a][b]) cudaEventDestroy(c.evk[a][b]);
+        if (c.stream) cudaStreamDestroy(c.stream);
+    }
+    g_ctx.free_list.clear();
+    return LICHEE_OK;
 }
 
 const char *lichee_last_error(void) { return g_err.c_str(); }

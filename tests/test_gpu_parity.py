@@ -310,3 +310,17 @@ def test_full_size_properties(built, n_clusters, n_samples, cap):
     kept = {(t.errorScore, t.seq) for t in th}
     assert set(best_possible) <= kept
     half.close()
+
+
+def test_grow_call_cap_and_memory_release(built):
+    """Parameters.MAX_NUM_GROW_CALLS stops the search at the first chunk boundary after the count of
+    accepted partial trees reaches it (status bit 2); the pooled buffers can be handed back."""
+    import lichee_b200
+    net, prm = make_instance(14, 6, seed=9)
+    st, trees, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 10, max_num_trees=10**12, max_num_grow_calls=5000)
+    assert st["status"] & 2 and st["num_grow_calls"] >= 5000
+    full, _, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 10, max_num_trees=10**12)
+    assert not (full["status"] & 3) and full["num_grow_calls"] > st["num_grow_calls"]
+    lichee_b200.release_cached_memory()
+    again, _, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 10, max_num_trees=10**12)
+    assert again["num_trees"] == full["num_trees"]
