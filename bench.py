@@ -123,6 +123,29 @@ def bundled_search_times(lichee_b200, with_cpu):
     return out
 
 
+def named_shape_times(lichee_b200, adj, vaf, margin, args):
+    """Search wall time, end to end from host arrays (median of 5), of (a) the headline network with the
+    REFERENCE'S OWN caps (MAX_NUM_TREES 100000, MAX_NUM_GROW_CALLS 1e8, -s 1000): what `-build` does
+    with this library in place of getLineageTrees; (b) BASELINE configs[3], 40 clusters x 20 samples,
+    -c, with the default caps and with the tree cap raised to 2^28."""
+    from lichee_b200.synth import make_instance
+    def timed(adj, vaf, margin, save, max_trees, max_grow=100000000):
+        ts, st = [], None
+        for _ in range(6):
+            t0 = time.perf_counter()
+            s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=save, max_num_trees=max_trees, max_num_grow_calls=max_grow)
+            st = s.run(); s.trees(); s.close()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        return {"e2e_ms": round(statistics.median(ts[1:]), 3), "valid_trees": int(st.num_trees), "checks": int(st.num_checks),
+                "status": int(st.status)}
+    out = {"120x64 default caps (-s 1000)": timed(adj, vaf, margin, args.save, 100000)}
+    net, prm = make_instance(40, 20, seed=args.seed)
+    v40 = np.ascontiguousarray(net.aaf, dtype=np.float64)
+    out["40x20 default caps (-s 100)"] = timed(net.adj, v40, prm.vaf_error_margin, 100, 100000)
+    out["40x20 max_trees 2^28, no grow-call cap (-s 100)"] = timed(net.adj, v40, prm.vaf_error_margin, 100, 1 << 28, 1 << 62)
+    return out
+
+
 def run_reference(args):
     """Reference arm: literal CPU port of PHYNetwork.grow on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -309,6 +332,7 @@ def main():
         }
         if world == 1:
             line["bundled_datasets_build_search_ms"] = bundled_search_times(lichee_b200, not args.no_cpu_baseline)
+            line["named_shapes"] = named_shape_times(lichee_b200, adj, vaf, margin, args)
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             t0 = time.perf_counter()

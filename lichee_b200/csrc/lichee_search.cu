@@ -13,13 +13,15 @@
 //   * One WARP extends one partial tree: lanes own samples (1 or 2 per lane), the centroid
 //     matrix lives in shared memory, the children of a candidate parent are found by comparing
 //     the item's parent bytes against the candidate and voting with __ballot_sync, and the
-//     per-sample sums are compared against parent VAF + margin with a warp vote.
+//     per-sample sums are compared against parent VAF + margin with a warp vote.  A warp walks a
+//     contiguous run of items and re-decides only what changed between lexicographic neighbours.
 //   * The frontier is kept in HBM level by level and walked depth-first in chunks, so memory is
 //     bounded by (levels x level_capacity) and trees come out in a deterministic canonical order.
 //     check -> exclusive scan -> emit keeps that order without atomics.
-//   * Complete trees are scored in double precision in the reference's accumulation order
-//     (parents by descending id, samples ascending, positive terms only) and filtered against
-//     the current s-th best score; survivors go through a block-level bitonic top-s selection.
+//   * The last level fuses check and scoring: complete trees are scored in double precision with a
+//     fixed-shape reduction, all trees of an item at once, and filtered against the current s-th
+//     best score without a square root; survivors go through an exact radix selection and a
+//     rank-merge into the device-resident ranked list.
 //   No tensor cores: nothing here is a dense contraction.  No CPU fallback.
 #include <cuda_runtime.h>
 
