@@ -324,3 +324,42 @@ def test_grow_call_cap_and_memory_release(built):
     lichee_b200.release_cached_memory()
     again, _, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 10, max_num_trees=10**12)
     assert again["num_trees"] == full["num_trees"]
+
+
+def test_randomized_stress_bit_exact_vs_canonical(built):
+    """150 seeded instances over node count, sample count (1..64), density, VAF scale, margin, -s,
+    tree cap and frontier capacity: CUDA == sequential canonical specification, bit for bit."""
+    rng = random.Random(20261019)
+    done = 0
+    for it in range(150):
+        n = rng.randint(2, 26)
+        S = rng.choice([1, 2, 3, 5, 8, 13, 20, 31, 32, 33, 47, 64])
+        adj, vaf = rand_dag(rng, n, S, rng.choice([0.15, 0.3, 0.6, 0.9]), rng.choice([0.05, 0.15, 0.3, 0.5]))
+        margin = rng.choice([0.0, 0.01, 0.1, 0.25])
+        cap = rng.choice([1, 3, 100, 5000, 40000])
+        kw = {}
+        if rng.random() < 0.4:
+            kw["level_capacity"] = rng.choice([1024, 2048, 8192])
+        assert_matches_canonical(adj, vaf, margin, num_save=rng.choice([1, 2, 33, 1000]), max_trees=cap, **kw)
+        done += 1
+    assert done == 150
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_mid_size_tree_set_vs_reference_search(built, seed):
+    """Sparser networks of 14-18 nodes on which the literal reference search still runs to completion
+    (10^4-10^6 trees): identical number of valid trees, identical ranked scores (1e-9)."""
+    rng = random.Random(500 + seed)
+    n = rng.randint(14, 18); S = rng.randint(2, 6)
+    adj, vaf = rand_dag(rng, n, S, 0.3, 0.05)
+    ref = oracle.search(adj, vaf, 0.1, top_s=1000, max_trees=3 * 10**6, max_grow=5 * 10**7, want_all=3 * 10**6)
+    if ref["stopped"]:
+        pytest.skip("reference search hit a cap on this instance")
+    st, trees, _ = gpu_search(adj, vaf, 0.1, 1000, max_num_trees=10**12)
+    assert st["num_trees"] == ref["n_trees"] > 5000
+    assert len(trees) == len(ref["scores"])
+    by_tree = {bytes(np.asarray(p, dtype=np.int32)): sc for p, sc in zip(ref["all_parents"], ref["all_scores"])}
+    for k, t in enumerate(trees):
+        assert abs(ref["scores"][k] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
+        key = bytes(np.asarray(t.parent, dtype=np.int32))
+        assert key in by_tree and abs(by_tree[key] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
