@@ -180,6 +180,24 @@ __device__ __forceinline__ void parent_presence(unsigned w, int rmax, unsigned p
     pm[3] = __reduce_or_sync(kFull, m3);
 }
 
+// Sum rule for candidate row q that already has children in item w: children + the new node (row
+// xv) against VAF(q) + margin in every sample.  One copy of the code (the kernels call it from
+// several unrolled places; inlined, they outgrow the instruction cache).
+template <int SPL>
+__device__ __noinline__ bool row_passes(unsigned w, unsigned q, int rmax, int W, const double *vaf_s, int SP, int lane,
+                                        double xv0, double xv1, double margin, bool valid0, bool valid1) {
+    double s0, s1, a0, a1;
+    child_sums<SPL>(w, q, rmax, W, vaf_s, SP, lane, s0, s1);
+    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
+    s0 = __dadd_rn(s0, xv0);
+    bool bad = valid0 && s0 > __dadd_rn(a0, margin);
+    if (SPL == 2) {
+        s1 = __dadd_rn(s1, xv1);
+        bad |= valid1 && s1 > __dadd_rn(a1, margin);
+    }
+    return !__any_sync(kFull, bad);
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel 1: sum-rule check.  One warp per frontier item; for every candidate parent of the node
 // placed at this level, test  sum(children VAF) + VAF(node) <= VAF(parent) + margin  per sample.
@@ -221,18 +239,8 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
 
-    // sum rule for candidate row q (present in the item): children + the new node against VAF(q) + margin
     auto passes = [&](unsigned w, unsigned q) {
-        double s0, s1, a0, a1;
-        child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
-        load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
-        s0 = __dadd_rn(s0, xv0);
-        bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
-        if (SPL == 2) {
-            s1 = __dadd_rn(s1, xv1);
-            bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
-        }
-        return !__any_sync(kFull, bad);
+        return row_passes<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1);
     };
 
     // Like the last-level kernel, a warp walks a contiguous run of items and, after the first one,
@@ -491,6 +499,29 @@ __device__ __forceinline__ double parent_excess(double s0, double s1, double a0,
     return butterfly_sum(t);
 }
 
+// One parent row of a leaf-parent item: excess E without the last node and, for a candidate parent,
+// the sum-rule check and the excess F with the last node added.  Returns the pass bit.
+template <int SPL>
+__device__ __noinline__ bool leaf_row(unsigned w, unsigned q, int rmax, int W, const double *vaf_s, int SP, int lane,
+                                      double xv0, double xv1, double margin, bool valid0, bool valid1, bool is_cand,
+                                      double &Eq, double &Fq) {
+    double s0, s1, a0, a1;
+    child_sums<SPL>(w, q, rmax, W, vaf_s, SP, lane, s0, s1);
+    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
+    Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+    Fq = 0.0;
+    if (!is_cand) return false;
+    s0 = __dadd_rn(s0, xv0);
+    bool bad = valid0 && s0 > __dadd_rn(a0, margin);
+    if (SPL == 2) {
+        s1 = __dadd_rn(s1, xv1);
+        bad |= valid1 && s1 > __dadd_rn(a1, margin);
+    }
+    if (__any_sync(kFull, bad)) return false;
+    Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+    return true;
+}
+
 // At the last level the sum-rule check and the scoring share all their sums, so one kernel does
 // both: it writes the pass mask + count of every item (for the scan that numbers the valid trees)
 // and appends the trees that beat the threshold with a provisional sequence number; seq_fixup_kernel
@@ -612,22 +643,8 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                     um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
                 }
                 if ((um[g] >> bq) & 1u) {                   // parent present in the item
-                    double s0, s1, a0, a1;
-                    child_sums<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, s0, s1);
-                    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
-                    Eq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
-                    if ((candq[g] >> bq) & 1u) {
-                        s0 = __dadd_rn(s0, xv0);
-                        bool bad = valid0 && s0 > __dadd_rn(a0, net.margin);
-                        if (SPL == 2) {
-                            s1 = __dadd_rn(s1, xv1);
-                            bad |= valid1 && s1 > __dadd_rn(a1, net.margin);
-                        }
-                        if (!__any_sync(kFull, bad)) {
-                            Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
-                            pass = true;
-                        }
-                    }
+                    pass = leaf_row<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1,
+                                         ((candq[g] >> bq) & 1u) != 0, Eq, Fq);
                 } else if (((candq[g] & okq[g]) >> bq) & 1u) {          // childless candidate: static
                     Fq = fstat_s[q];
                     pass = true;
