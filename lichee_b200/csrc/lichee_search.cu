@@ -1428,9 +1428,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // first full item, short enough to keep every warp slot of the grid busy
             const int grid = grid_for(B);
             // several runs per warp (load balance between cheap and expensive runs), each 16..64 items long
-            static const int env_runs = getenv("LICHEE_RUNS_PER_WARP") ? atoi(getenv("LICHEE_RUNS_PER_WARP")) : 1;
-            static const int env_minrun = getenv("LICHEE_MIN_RUN") ? atoi(getenv("LICHEE_MIN_RUN")) : 1;
-            int run_len = (int)std::min<long long>(64, std::max<long long>(env_minrun, B / ((long long)grid * kWarpsPerBlock * env_runs)));
+            // (measured: one run per warp beats several shorter runs, and chunks that stay L2-resident
+            //  beat larger ones -- profiles/README.md)
+            int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
             if (run_len > B) run_len = (int)std::max<long long>(1, B);
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, B, h->head[lv], h->d_mask(), h->d_cnt(), R, h->d_meta(), h->prm.num_save,
@@ -1763,7 +1763,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
     h->chunk_max = std::min<long long>(h->cap, 1ll << 20);
-    h->cand_cap = std::max<long long>(h->cap, getenv("LICHEE_CAND_CAP_LOG2") ? 1ll << atoi(getenv("LICHEE_CAND_CAP_LOG2")) : 1ll << 23);
+    h->cand_cap = std::max<long long>(h->cap, 1ll << 23);
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
     CKE(ensure(h, h->b_small, 256));
