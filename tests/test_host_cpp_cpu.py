@@ -71,3 +71,36 @@ def test_cli_rejects_bad_input(built, tmp_path):
     assert r.returncode == 1 and "Wrong input file format" in r.stderr
     r = subprocess.run([CLI, "-build", "-i", str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and "normal sample id" in r.stderr
+
+
+def test_readme_example_with_sample_profile_and_clusters_file(built, tmp_path):
+    """The example input of the reference README ('Input File Types'): SSNV file with a presence
+    profile column (-sampleProfile) and the matching 3-line clusters file (-clustersFile)."""
+    snv = ("#chr\tposition\tdescription\tprofile\tNormal\tS1\tS2\tS3\tS4\n"
+           "1\t184306474\tA/G HMCN1\t01111\t0.0\t0.1\t0.2\t0.25\t0.15\n"
+           "1\t18534005\tC/A IGSF21\t01111\t0.0\t0.1\t0.25\t0.2\t0.1\n"
+           "1\t110456920\tG/A UBL4B\t01111\t0.0\t0.4\t0.4\t0.45\t0.45\n"
+           "10\t26503064\tC/G MYO3A\t01001\t0.0\t0.4\t0.0\t0.0\t0.24\n")
+    clu = ("01111\t0.0\t0.1\t0.23\t0.23\t0.13\t1,2\n"
+           "01111\t0.0\t0.4\t0.4\t0.45\t0.45\t3\n"
+           "01001\t0.0\t0.4\t0.0\t0.0\t0.24\t4\n")
+    (tmp_path / "snv.txt").write_text(snv)
+    (tmp_path / "clu.txt").write_text(clu)
+    out = tmp_path / "net.txt"
+    subprocess.run([CLI, "-build", "-i", str(tmp_path / "snv.txt"), "-sampleProfile", "-clustersFile", str(tmp_path / "clu.txt"),
+                    "-dumpNetwork", str(out)], check=True, capture_output=True)
+    tags, sizes, aaf, adj = parse_dump(out)
+    assert sorted(tags[1:]) == ["01001", "01111", "01111"] and sorted(sizes[1:]) == [1, 1, 2]
+    by = {(t, s): row for t, s, row in zip(tags, sizes, aaf)}
+    assert by[("01111", 2)] == [0.0, 0.1, 0.23, 0.23, 0.13]
+    assert by[("01001", 1)] == [0.0, 0.4, 0.0, 0.0, 0.24]
+    n = len(tags)
+    indeg = [0] * n
+    for ch in adj:
+        for c in ch:
+            indeg[c] += 1
+    assert indeg[0] == 0 and all(d >= 1 for d in indeg[1:])       # every cluster node has a parent
+    # the larger 4-sample cluster (0.4 ...) can be the parent of the smaller one and of the 2-sample cluster
+    big = tags.index("01111") if sizes[tags.index("01111")] == 1 and aaf[tags.index("01111")][1] == 0.4 else \
+        [i for i in range(1, n) if tags[i] == "01111" and aaf[i][1] == 0.4][0]
+    assert len(adj[big]) >= 1
