@@ -116,11 +116,31 @@ __device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b) {
     return a.seq < b.seq;
 }
 
-// Shared-memory staging of the centroid matrix and the candidate table of one level.
+// Shared-memory staging of the centroid matrix and the candidate table of one level.  The matrix (up
+// to 64 KB) comes in with ONE TMA bulk copy (cp.async.bulk -> SASS UBLKCP) that completes on an
+// mbarrier, instead of every thread looping over it; the 128-byte candidate table is loaded by the
+// threads while the copy is in flight.
 __device__ __forceinline__ void stage_network(const DevNet &net, int level, double *vaf_s, uint8_t *cand_s) {
-    const int words = net.n * net.SP;
-    for (int i = threadIdx.x; i < words; i += blockDim.x) vaf_s[i] = net.vaf[i];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    const unsigned dst_a = (unsigned)__cvta_generic_to_shared(vaf_s);
+    const unsigned bytes = (unsigned)(net.n * net.SP * sizeof(double));   // multiple of 256
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(net.vaf), "r"(bytes), "r"(bar_a) : "memory");
+    }
     for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) cand_s[i] = net.cand[(size_t)level * kMaxN + i];
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_a) : "memory");
+    }
     __syncthreads();
 }
 
