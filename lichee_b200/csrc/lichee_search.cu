@@ -956,23 +956,34 @@ struct RadixState {
     unsigned long long k;           // rank still to find inside the current prefix bucket
     unsigned hist[256];
     unsigned long long kept;        // candidates compacted
+    unsigned blocks_done;           // last-block-done counter of the current pass
+    unsigned ties_fit;              // set after the score passes when every tie at the threshold can be kept
+    unsigned long long below;       // candidates with a score below the threshold
 };
 
 __global__ void radix_init(RadixState *st, unsigned long long k) {
     st->prefix[0] = st->prefix[1] = 0;
     st->k = k;
     st->kept = 0;
+    st->blocks_done = 0;
+    st->ties_fit = 0;
+    st->below = 0;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) st->hist[i] = 0;
 }
 
+// One pass = one launch: every block histograms its share of the candidates for the current byte; the
+// last block to finish picks the bucket that holds the k-th smallest key and clears the histogram.
 // pass 0..7: bytes of the score (high to low); pass 8..15: bytes of seq among candidates whose score
-// equals the selected one.  (part is constant inside one handle's candidate list.)
+// equals the selected one (skipped when all ties at the threshold fit in the rank-merge tile anyway).
+// (part is constant inside one handle's candidate list.)
 __global__ void __launch_bounds__(256)
-radix_hist(const Cand *__restrict__ cands, long long m, RadixState *st, int pass) {
+radix_pass(const Cand *__restrict__ cands, long long m, RadixState *st, int pass, unsigned tile) {
     __shared__ unsigned h[256];
+    __shared__ bool last;
+    const int word = pass >> 3, shift = 56 - 8 * (pass & 7);
+    if (word == 1 && st->ties_fit) return;                    // uniform for the whole grid
     h[threadIdx.x] = 0;
     __syncthreads();
-    const int word = pass >> 3, shift = 56 - 8 * (pass & 7);
     const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
     const unsigned long long himask = (pass & 7) == 0 ? 0ull : ~0ull << (shift + 8);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
@@ -987,16 +998,20 @@ radix_hist(const Cand *__restrict__ cands, long long m, RadixState *st, int pass
     }
     __syncthreads();
     if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
-}
-
-__global__ void radix_pick(RadixState *st, int pass) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    h[threadIdx.x] = *(volatile unsigned *)&st->hist[threadIdx.x];     // whole histogram, one load per thread
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const int word = pass >> 3, shift = 56 - 8 * (pass & 7);
         unsigned long long k = st->k, run = 0;
         int b = 0;
         for (; b < 256; b++) {
-            if (run + st->hist[b] >= k) break;
-            run += st->hist[b];
+            if (run + h[b] >= k) break;
+            run += h[b];
         }
         if (b == 256) {                               // fewer than k candidates: keep everything
             st->prefix[word] |= 0xffull << shift;
@@ -1004,7 +1019,14 @@ __global__ void radix_pick(RadixState *st, int pass) {
         } else {
             st->prefix[word] |= (unsigned long long)b << shift;
             st->k = k - run;
+            if (word == 0) st->below += run;
+            if (pass == 7) {
+                // every candidate with exactly the threshold score: if they all fit next to the ones
+                // below it, keep them all and let the rank-merge order them -- no seq passes needed
+                if (st->below + h[b] <= (unsigned long long)tile) { st->ties_fit = 1; st->prefix[1] = ~0ull; }
+            }
         }
+        st->blocks_done = 0;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) st->hist[i] = 0;
@@ -1265,14 +1287,12 @@ int run_radix_select(lichee_search *h, long long &m, bool &used) {
     RadixState *st = static_cast<RadixState *>(h->b_radix.p);
     const int grid = (int)std::min<long long>((m + 255) / 256, 148 * 8);
     radix_init<<<1, 256, 0, h->stream>>>(st, (unsigned long long)h->prm.num_save);
-    for (int pass = 0; pass < 16; pass++) {
-        radix_hist<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, pass);
-        radix_pick<<<1, 256, 0, h->stream>>>(st, pass);
-    }
+    for (int pass = 0; pass < 16; pass++)
+        radix_pass<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, pass, (unsigned)kSelTile);
     radix_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, h->d_cands(1), (long long)kSelTile);
     CK(cudaGetLastError());
-    h->stats.num_launches += 34;
-    h->stats.kernel_launches[LICHEE_K_SELECT] += 34;
+    h->stats.num_launches += 18;
+    h->stats.kernel_launches[LICHEE_K_SELECT] += 18;
     unsigned long long kept = 0;
     CK(cudaMemcpyAsync(&kept, &st->kept, sizeof(kept), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
