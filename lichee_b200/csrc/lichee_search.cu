@@ -784,10 +784,11 @@ __global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, 
 // (ties: lower part, then lower seq wins), then gathers the surviving trees' parent bytes into
 // the other half of the double-buffered tree store.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bitonic_sort_2048(Cand *e) {
-    for (int k = 2; k <= 2 * kSelTile; k <<= 1) {
+template <int N>
+__device__ __forceinline__ void bitonic_sort(Cand *e) {
+    for (int k = 2; k <= N; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < 2 * kSelTile; t += kSelThreads) {
+            for (int t = threadIdx.x; t < N; t += kSelThreads) {
                 const int x = t ^ j;
                 if (x > t) {
                     const bool up = (t & k) == 0;
@@ -829,7 +830,7 @@ select_reduce_kernel(const Cand *__restrict__ in, long long m, Cand *__restrict_
         for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
             e[kSelTile + t] = base + t < hi ? in[base + t] : sentinel;
         __syncthreads();
-        bitonic_sort_2048(e);
+        bitonic_sort<2 * kSelTile>(e);
     }
     for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) out[(long long)blockIdx.x * kSelTile + t] = e[t];
 }
@@ -874,27 +875,28 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         fresh[t] = t < mm ? cands[t] : sentinel;
         out[t] = sentinel;
         __syncthreads();
+        // sort the fresh candidates, then every entry's final position is its own index plus the
+        // number of entries of the OTHER list that are smaller (binary search; keys are unique)
+        bitonic_sort<kSelTile>(fresh);
         const Cand mine_old = e[t], mine_new = fresh[t];
-        const bool has_old = (unsigned)t < count, has_new = t < mm && mine_new.pad == 0;
-        unsigned below_old = 0, below_new = 0;      // fresh entries smaller than my old / my new entry
-        for (int j = 0; j < mm; j++) {
-            const Cand c = fresh[j];
-            if (c.pad) continue;
-            below_old += cand_less(c, mine_old);
-            below_new += cand_less(c, mine_new);
-        }
+        const bool has_old = (unsigned)t < count, has_new = mine_new.pad == 0;
         if (has_new) {
             int lo = 0, hi = (int)count;            // old entries smaller than my new entry
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (cand_less(e[mid], mine_new)) lo = mid + 1; else hi = mid;
             }
-            const unsigned pos = (unsigned)lo + below_new;
+            const unsigned pos = (unsigned)t + (unsigned)lo;
             if (pos < (unsigned)kSelTile) out[pos] = mine_new;
             atomicAdd(&real_n, 1u);
         }
         if (has_old) {
-            const unsigned pos = (unsigned)t + below_old;
+            int lo = 0, hi = kSelTile;              // fresh entries smaller than my old entry (sentinels sort last)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cand_less(fresh[mid], mine_old)) lo = mid + 1; else hi = mid;
+            }
+            const unsigned pos = (unsigned)t + (unsigned)lo;
             if (pos < (unsigned)kSelTile) out[pos] = mine_old;
             atomicAdd(&real_n, 1u);
         }
@@ -905,7 +907,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
             for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
                 e[kSelTile + t] = base + t < m ? cands[base + t] : sentinel;
             __syncthreads();
-            bitonic_sort_2048(e);
+            bitonic_sort<2 * kSelTile>(e);
         }
         // candidates may contain sentinel padding written by the tournament: count the real entries
         unsigned mine = 0;
