@@ -486,8 +486,9 @@ emit_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel 4: score complete trees.  One warp per leaf-parent item (every node placed but the last);
-// every passing choice p* for the last node is a complete valid tree.
+// kernel 4: last level, sum-rule check and scoring fused.  A warp walks a contiguous run of
+// leaf-parent items (every node placed but the last); every passing choice p* for the last node is a
+// complete valid tree.
 //   score = sqrt( sum over parents p, samples s of max(0, sum(children of p)[s] - VAF(p)[s])^2 )
 // (PHYTree.computeErrorScore, PHYTree.java:214-233).  The reference adds the positive terms one
 // after another; with noisy centroids a tree has thousands of them, i.e. thousands of dependent
@@ -780,9 +781,11 @@ __global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, 
 
 // ------------------------------------------------------------------------------------------
 // kernel 5: block-level top-s selection.  One block keeps the ranked list (<= 1024 trees) in
-// shared memory, streams the candidates through it in tiles with a bitonic sort of 2048 entries
-// (ties: lower part, then lower seq wins), then gathers the surviving trees' parent bytes into
-// the other half of the double-buffered tree store.
+// shared memory.  Up to 1024 new candidates (the usual case, after the radix pre-selection) are
+// sorted and rank-merged with binary searches; longer lists are streamed through in tiles with a
+// bitonic sort of 2048 entries.  Keys are (score, part, seq): ties in score go to the earlier tree of
+// the canonical order.  The survivors' parent bytes are gathered into the other half of the
+// double-buffered tree store and the new threshold is published.
 // ------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void bitonic_sort(Cand *e) {
