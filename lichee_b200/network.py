@@ -1,6 +1,7 @@
-"""Pure-Python restatement of the reference code on either side of the tree search
-: SSNV loading/calling and constraint-network
-construction -- the host-side data path on the input side of the tree search (DESIGN.md row f).
+"""Pure-Python restatement of the reference code on the input side of the tree search: SSNV
+loading and calling, grouping, cluster collapse and constraint-network construction (DESIGN.md row f).
+Independent of the C++ host mirror (csrc/lichee_host.cpp); the tests require the two to agree bit for
+bit on every bundled dataset.  Used to build fixtures and the synthetic workloads.
 
 Reference (read-only):
   SNVDataStore.loadSNVFile / parseSNVEntry / processSNVEntry   SNVDataStore.java:385-409,522-545,663-718
