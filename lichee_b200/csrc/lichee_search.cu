@@ -103,6 +103,7 @@ struct TopMeta {             // device-resident state of the ranked list
     double tau;              // score of the worst held tree once the list is full, else +inf
     unsigned long long n_cand;  // candidates appended by the current leaf launch
     unsigned long long n_valid; // valid complete trees counted by the current leaf launch
+    unsigned long long next_run; // work queue of the current leaf launch: next unclaimed run of items
 };
 
 struct ScanOut {             // written by the scan, read back by the host once per chunk
@@ -596,8 +597,6 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             t = __longlong_as_double(__double_as_longlong(t) + 1);
         tmax = __dsqrt_rn(t) < tau ? t : -1.0;             // tau == 0: nothing can beat it
     }
-    const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     unsigned long long my_valid = 0;
 
     // A warp walks a contiguous run of items.  Neighbours in the canonical order differ in very few
@@ -608,7 +607,12 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};   // pb: pass bits by candidate index
     unsigned w_prev = 0;
-    for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len) {
+    // runs are handed out from a counter, so a warp that drew cheap runs simply draws more of them
+    for (;;) {
+    long long run0 = 0;
+    if (lane == 0) run0 = (long long)atomicAdd(&meta->next_run, 1ull) * run_len;
+    run0 = __shfl_sync(kFull, run0, 0);
+    if (run0 >= n_items) break;
     const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
     unsigned w_next = lane < wstride ? __ldg(items + run0 * wstride + lane) : 0xffffffffu;
     for (long long it = run0; it < run1; it++) {
@@ -945,6 +949,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
         meta->n_valid = 0;
+        meta->next_run = 0;
     }
 }
 
@@ -1051,7 +1056,7 @@ radix_compact(const Cand *__restrict__ cands, long long m, RadixState *st, Cand 
     }
 }
 
-__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; }
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -1059,6 +1064,7 @@ __global__ void init_meta(TopMeta *meta) {
     meta->tau = INFINITY;
     meta->n_cand = 0;
     meta->n_valid = 0;
+    meta->next_run = 0;
 }
 
 // unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
@@ -1473,8 +1479,8 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // first full item, short enough to keep every warp slot of the grid busy
             const int grid = grid_for(B);
             // several runs per warp (load balance between cheap and expensive runs), each 16..64 items long
-            // (measured: one run per warp beats several shorter runs, and chunks that stay L2-resident
-            //  beat larger ones -- profiles/README.md)
+            // (measured: run lengths 16..48 perform alike once runs are claimed dynamically, and chunks
+            //  that stay L2-resident beat larger ones -- profiles/README.md)
             int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
             if (run_len > B) run_len = (int)std::max<long long>(1, B);
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
