@@ -137,7 +137,7 @@ def named_shape_times(lichee_b200, adj, vaf, margin, args):
             st = s.run(); s.trees(); s.close()
             ts.append(1e3 * (time.perf_counter() - t0))
         return {"e2e_ms": round(statistics.median(ts[1:]), 3), "valid_trees": int(st.num_trees), "checks": int(st.num_checks),
-                "status": int(st.status)}
+                "status": int(st.status), "launches": int(st.num_launches), "device_ms": round(float(st.kernel_ms_total), 3)}
     out = {"120x64 default caps (-s 1000)": timed(adj, vaf, margin, args.save, 100000)}
     net, prm = make_instance(40, 20, seed=args.seed)
     v40 = np.ascontiguousarray(net.aaf, dtype=np.float64)

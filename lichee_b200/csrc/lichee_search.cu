@@ -1479,9 +1479,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // first full item, short enough to keep every warp slot of the grid busy
             const int grid = grid_for(B);
             // several runs per warp (load balance between cheap and expensive runs), each 16..64 items long
-            // (measured: run lengths 16..48 perform alike once runs are claimed dynamically, and chunks
-            //  that stay L2-resident beat larger ones -- profiles/README.md)
-            int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
+            // (measured: run lengths 16..36 perform alike once runs are claimed dynamically, longer ones
+            //  lose to the tail; chunks that stay L2-resident beat larger ones -- profiles/README.md)
+            int run_len = (int)std::min<long long>(32, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
             if (run_len > B) run_len = (int)std::max<long long>(1, B);
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, B, h->head[lv], h->d_mask(), h->d_cnt(), R, h->d_meta(), h->prm.num_save,
