@@ -239,7 +239,7 @@ class LineageSearch:
         seq = np.zeros(m, dtype=np.int64)
         _ck(lib().lichee_search_get_trees(self._h, 0, m, sc.ctypes.data, par.ctypes.data, order.ctypes.data,
                                           seq.ctypes.data))
-        return [PHYTree(sc[k], par[k], order[k], seq[k]) for k in range(m)]
+        return [PHYTree(*t) for t in zip(sc.tolist(), par, order, seq.tolist())]
 
     def record_bytes(self):
         return int(lib().lichee_record_bytes(self._h))

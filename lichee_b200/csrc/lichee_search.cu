@@ -487,6 +487,256 @@ emit_kernel(DevNet net, int level, const unsigned *__restrict__ items, long long
 }
 
 // ------------------------------------------------------------------------------------------
+// kernel 3b: device-side depth-first scheduling of NARROW chunks.  While the frontier is a handful of
+// items per level (the first descent of every search, the whole search of a real-data network) a
+// host-driven check -> scan -> emit costs three launches and one host round trip per tree level, ~60 us
+// for a few microseconds of work.  Here ONE block stages the centroid matrix once and then runs the
+// driver loop itself: pick the deepest non-empty level, size the chunk with the same budget rule as the
+// host, check (one warp per (item, slice of the candidate list)), scan in one warp, emit, repeat.  It
+// returns to the host when the deepest level is the last one (the fused check+score kernel takes
+// over), when a chunk would be wide enough for the grid-wide kernels, or when the search is over.
+// Children are written in canonical order like the wide path, so which path ran a chunk is invisible
+// in the results.
+// ------------------------------------------------------------------------------------------
+constexpr int kNarrowThreads = 1024;
+constexpr int kNarrowWarps = kNarrowThreads / 32;
+constexpr int kNarrowMax = 128;        // items per narrow chunk
+constexpr int kNarrowCap = 2048;       // children a narrow chunk may emit (every level buffer holds at least this many)
+constexpr int kNarrowIters = 8192;     // chunks per launch (keeps the host's view of the counters fresh)
+
+enum { kStopDone = 0, kStopLeaf = 1, kStopWide = 2, kStopGrow = 3, kStopIters = 4 };
+
+struct Sched {                         // scheduler state, uploaded before and read back after a launch
+    long long head[kMaxN], tail[kMaxN];
+    unsigned *ptr[kMaxN];              // level buffers
+    double fan[kMaxN];                 // observed mean number of surviving children per item of a level
+    int seen[kMaxN];
+    long long trees_left;              // max_num_trees - valid trees found so far
+    long long grow_calls, max_grow_calls;
+    long long chunk_max, cap;
+    long long checks, frontier_bytes, check_bytes, emit_bytes, chunks;
+    int stop, stop_level;
+};
+
+template <int SPL>
+__global__ void __launch_bounds__(kNarrowThreads, 1)
+descend_kernel(DevNet net, Sched *sc) {
+    // dynamic shared memory: centroid matrix | 128 bytes (stage_network's table slot) | candidate tables of
+    // every level
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vaf_s = reinterpret_cast<double *>(smem_raw);
+    uint8_t *cand0_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    uint8_t *cand_all = cand0_s + kMaxN;                                  // [L][128]
+    __shared__ long long head_s[kMaxN], tail_s[kMaxN];
+    __shared__ double fan_s[kMaxN];
+    __shared__ int seen_s[kMaxN];
+    __shared__ uint8_t ncand_s[kMaxN];
+    __shared__ signed char rmax_s[kMaxN];                                 // highest byte lane in use at a level
+    __shared__ uint8_t wl_s[kMaxN], sh_s[kMaxN];                          // word / bit shift of a level's own byte
+    __shared__ unsigned *ptr_s[kMaxN];
+    __shared__ unsigned item_s[kNarrowMax * 32];                          // the chunk's items
+    __shared__ unsigned mask_s[kNarrowMax * 4], cnt_s[kNarrowMax], off_s[kNarrowMax];
+    __shared__ int lv_s, B_s, stop_s, nfit_s;
+    __shared__ unsigned total_s;
+
+    const int L = net.L;
+    const int W = net.stride >> 2;
+    stage_network(net, 0, vaf_s, cand0_s);
+    for (int i = threadIdx.x; i < L * (kMaxN / 4); i += blockDim.x)
+        reinterpret_cast<unsigned *>(cand_all)[i] = reinterpret_cast<const unsigned *>(net.cand)[i];
+    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) {
+        head_s[i] = sc->head[i]; tail_s[i] = sc->tail[i]; fan_s[i] = sc->fan[i]; seen_s[i] = sc->seen[i];
+        ncand_s[i] = i < L ? net.ncand[i] : 0;
+        ptr_s[i] = sc->ptr[i];
+        rmax_s[i] = (signed char)(i > 0 ? (i - 1) / W : -1);
+        wl_s[i] = (uint8_t)(item_byte(i, W) >> 2);
+        sh_s[i] = (uint8_t)(8 * (item_byte(i, W) & 3));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int SP = net.SP;
+    const bool valid0 = lane < net.S;
+    const bool valid1 = SPL == 2 && lane + 32 < net.S;
+    const long long cap = sc->cap, chunk_max = sc->chunk_max, trees_left = sc->trees_left, max_grow = sc->max_grow_calls;
+    const long long limit = cap < (long long)kNarrowCap ? cap : (long long)kNarrowCap;
+    // scheduler registers (meaningful in warp 0 only)
+    long long grow = sc->grow_calls, checks = 0, fbytes = 0, cbytes = 0, ebytes = 0, chunks = 0;
+    int hint = L - 1;                  // every level deeper than this is empty
+
+    // Warp 0 picks the next chunk: deepest non-empty level, sized by the host's rule (run_search): what is
+    // pending, cut to what the remaining tree budget can use and to what the next level is expected to hold.
+    auto schedule = [&](int iter) {
+        int lv = -1;
+        for (int l = hint; l >= 0; l--) if (tail_s[l] > head_s[l]) { lv = l; break; }
+        int stop = -1;
+        long long B = 0;
+        if (lv < 0) stop = kStopDone;
+        else if (lv == L - 1) stop = kStopLeaf;
+        else if (grow >= max_grow) stop = kStopGrow;
+        else if (iter >= kNarrowIters) stop = kStopIters;
+        else {
+            // expected complete trees below one item of this level: product of the fan-outs from here down
+            double prod = 1.0;
+            for (int l = lv + lane; l < L; l += 32) prod *= fmax(seen_s[l] ? fan_s[l] : (double)ncand_s[l], 1e-3);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) prod *= __shfl_xor_sync(kFull, prod, d);
+            const double yield = fmin(1e30, prod);
+            const long long pending = tail_s[lv] - head_s[lv];
+            B = pending < chunk_max ? pending : chunk_max;
+            const double want = 1.25 * (double)trees_left / yield + 8.0;
+            if ((double)B > want) B = (long long)want;
+            const long long guess = (long long)(0.8 * (double)cap / fmax(1.0, fan_s[lv]));
+            const long long gmax = guess > 1024 ? guess : 1024;
+            if (B > gmax) B = gmax;
+            if (B < 1) B = 1;
+            if (B > kNarrowMax) {
+                if (iter == 0) B = kNarrowMax;      // the host asked for this chunk: always make progress
+                else stop = kStopWide;
+            }
+        }
+        if (lane == 0) { lv_s = lv; B_s = (int)B; stop_s = stop; }
+    };
+    if (wid == 0) schedule(0);
+    __syncthreads();
+
+    for (int iter = 1; stop_s < 0; iter++) {
+        const int lv = lv_s, B = B_s;
+        const int k = ncand_s[lv];
+        const uint8_t *cand_s = cand_all + (size_t)lv * kMaxN;
+        const int rmax = rmax_s[lv];
+        {
+            // stage the chunk's items (plain loads through L2: they may have been written by this block)
+            const unsigned *items = ptr_s[lv] + (size_t)head_s[lv] * W;
+            for (int i = threadIdx.x; i < B * 32; i += blockDim.x)
+                if ((i & 31) < W) item_s[i] = __ldcg(items + (size_t)(i >> 5) * W + (i & 31));
+            for (int i = threadIdx.x; i < B * 4; i += blockDim.x) mask_s[i] = 0;
+        }
+        __syncthreads();
+
+        // check: a task is (item, slice of the candidate list); few items -> more slices per item.  Every
+        // candidate goes through the sums (a candidate without children gives 0 + VAF(node) against
+        // VAF(parent) + margin, the same doubles as the static bit of the wide kernels).
+        int lp = 0;
+        while (lp < 3 && (B << (lp + 1)) <= 2 * kNarrowWarps && (2 << lp) <= k) lp++;
+        for (int task = wid; task < (B << lp); task += kNarrowWarps) {
+            const int it = task >> lp, part = task & ((1 << lp) - 1);
+            const int c0 = (k * part) >> lp, c1 = (k * (part + 1)) >> lp;
+            const unsigned w = lane < W ? item_s[it * 32 + lane] : 0xffffffffu;
+            double xv0, xv1;
+            load_row<SPL>(vaf_s, lv + 1, SP, lane, xv0, xv1);
+            unsigned long long blo = 0, bhi = 0;
+            for (int j = c0; j < c1; j++) {
+                const bool pass = row_passes<SPL>(w, cand_s[j], rmax, W, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1);
+                const unsigned long long bit = (unsigned long long)(pass ? 1u : 0u) << (j & 63);
+                if (j < 64) blo |= bit; else bhi |= bit;
+            }
+            if (lane == 0) {
+                if ((unsigned)blo) atomicOr(&mask_s[it * 4 + 0], (unsigned)blo);
+                if ((unsigned)(blo >> 32)) atomicOr(&mask_s[it * 4 + 1], (unsigned)(blo >> 32));
+                if ((unsigned)bhi) atomicOr(&mask_s[it * 4 + 2], (unsigned)bhi);
+                if ((unsigned)(bhi >> 32)) atomicOr(&mask_s[it * 4 + 3], (unsigned)(bhi >> 32));
+            }
+        }
+        __syncthreads();
+
+        // scan (one warp, four items per lane): child offsets in canonical order and the longest prefix
+        // of items whose children fit the next level
+        if (wid == 0) {
+            unsigned v[4], run = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int idx = lane * 4 + i;
+                v[i] = idx < B ? __popc(mask_s[idx * 4]) + __popc(mask_s[idx * 4 + 1]) + __popc(mask_s[idx * 4 + 2]) + __popc(mask_s[idx * 4 + 3]) : 0u;
+                run += v[i];
+            }
+            unsigned inc = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += t;
+            }
+            unsigned ex = inc - run;
+            int fit = 0;
+            unsigned fit_total = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int idx = lane * 4 + i;
+                if (idx < B) {
+                    cnt_s[idx] = v[i];
+                    off_s[idx] = ex;
+                    ex += v[i];
+                    if ((long long)ex <= limit) { fit = idx + 1; fit_total = ex; }
+                }
+            }
+            // inclusive sums are non-decreasing, so the fitting prefix is the largest fitting index
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const int f2 = __shfl_xor_sync(kFull, fit, d);
+                const unsigned t2 = __shfl_xor_sync(kFull, fit_total, d);
+                if (f2 > fit) { fit = f2; fit_total = t2; }
+            }
+            if (lane == 0) { nfit_s = fit; total_s = fit_total; }
+        }
+        __syncthreads();
+
+        const int n_fit = nfit_s;
+        const unsigned total_fit = total_s;
+        unsigned *out = ptr_s[lv + 1];
+        if (wid == 0) {
+            // book the chunk and choose the next one while the other warps emit
+            if (lane == 0) {
+                head_s[lv] += n_fit;
+                if (head_s[lv] == tail_s[lv]) head_s[lv] = tail_s[lv] = 0;
+                head_s[lv + 1] = 0;
+                tail_s[lv + 1] = total_fit;
+                const double f = (double)total_fit / (double)n_fit;
+                fan_s[lv] = seen_s[lv] ? 0.5 * fan_s[lv] + 0.5 * f : f;
+                seen_s[lv] = 1;
+            }
+            checks += (long long)n_fit * k;
+            grow += total_fit;
+            fbytes += ((long long)n_fit + total_fit) * net.stride;
+            cbytes += (long long)n_fit * (net.stride + 20);
+            ebytes += (long long)n_fit * (net.stride + 20) + (long long)total_fit * net.stride;
+            chunks += 1;
+            hint = lv + 1;
+            __syncwarp();
+            schedule(iter);            // writes lv_s / B_s / stop_s: read by the block after the barrier below
+        }
+        // emit: the surviving children of the fitting items, one coalesced line each
+        {
+            const int wl = wl_s[lv], sh = sh_s[lv];
+            for (int it = wid; it < n_fit; it += kNarrowWarps) {
+                if (cnt_s[it] == 0) continue;
+                const unsigned w = lane < W ? item_s[it * 32 + lane] : 0xffffffffu;
+                size_t dst = off_s[it];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    unsigned b = mask_s[it * 4 + g];
+                    while (b) {
+                        const int i = g * 32 + __ffs(b) - 1;
+                        b &= b - 1;
+                        unsigned cw = w;
+                        if (lane == wl) cw = (w & ~(0xffu << sh)) | ((unsigned)cand_s[i] << sh);
+                        if (lane < W) out[dst * W + lane] = cw;
+                        dst++;
+                    }
+                }
+            }
+        }
+        __syncthreads();     // the emitted items are visible to the whole block from here on
+    }
+    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) {
+        sc->head[i] = head_s[i]; sc->tail[i] = tail_s[i]; sc->fan[i] = fan_s[i]; sc->seen[i] = seen_s[i];
+    }
+    if (threadIdx.x == 0) {
+        sc->grow_calls = grow; sc->checks = checks; sc->frontier_bytes = fbytes;
+        sc->check_bytes = cbytes; sc->emit_bytes = ebytes; sc->chunks = chunks;
+        sc->stop = stop_s; sc->stop_level = lv_s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel 4: last level, sum-rule check and scoring fused.  A warp walks a contiguous run of
 // leaf-parent items (every node placed but the last); every passing choice p* for the last node is a
 // complete valid tree.
@@ -1173,6 +1423,7 @@ CtxPool g_ctx;
 struct DevBuf {              // one growable device buffer owned by a handle
     void *p = nullptr;
     size_t bytes = 0;
+    bool view = false;       // points into the handle's level slab: not returned to the pool
 };
 
 }  // namespace
@@ -1193,8 +1444,12 @@ struct lichee_search {
     long long cap = 0;                       // upper bound on items per level buffer
     long long cand_cap = 0;                  // upper bound on candidates one last-level launch may append
     DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_cands[2], b_top[2], b_tree[2];
+    DevBuf b_slab;                           // kNarrowCap items for every level (what the narrow scheduler emits into)
+    DevBuf b_sched;                          // Sched, device copy
     ScanOut *h_scan = nullptr;               // pinned
     TopMeta *h_meta = nullptr;               // pinned
+    Sched *h_sched = nullptr;                // pinned
+    bool narrow = true;                      // device-side scheduling of narrow chunks (LICHEE_NO_NARROW=1 turns it off)
     int flip = 0;
     long long chunk_max = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1224,8 +1479,8 @@ namespace {
 // make `b` at least `bytes` large; contents are NOT preserved (callers only grow empty buffers)
 int ensure(lichee_search *h, DevBuf &b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return LICHEE_OK;
-    if (b.p) g_pool.put(h->device, b.p, b.bytes);
-    b.p = nullptr; b.bytes = 0;
+    if (b.p && !b.view) g_pool.put(h->device, b.p, b.bytes);
+    b.p = nullptr; b.bytes = 0; b.view = false;
     size_t got = 0;
     CK(g_pool.get(h->device, bytes, &b.p, &got));
     b.bytes = got;
@@ -1233,8 +1488,8 @@ int ensure(lichee_search *h, DevBuf &b, size_t bytes) {
 }
 
 void give_back(lichee_search *h, DevBuf &b) {
-    g_pool.put(h->device, b.p, b.bytes);
-    b.p = nullptr; b.bytes = 0;
+    if (!b.view) g_pool.put(h->device, b.p, b.bytes);
+    b.p = nullptr; b.bytes = 0; b.view = false;
 }
 
 int grid_for(long long items) {
@@ -1447,7 +1702,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             double yield = 1.0;
             for (int l = lv; l < L; l++)   // unseen levels: assume every candidate passes, so the first descent stays narrow
                 yield = std::min(1e30, yield * std::max(seen[l] ? fan[l] : (double)h->cands[l].size(), 1e-3));
-            const double want = 1.25 * (double)(h->prm.max_num_trees - seq_base) / yield + 64.0;
+            const double want = 1.25 * (double)(h->prm.max_num_trees - seq_base) / yield + 8.0;
             if ((double)B > want) B = (long long)want;
         }
         if (!leaf) {
@@ -1458,6 +1713,44 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             B = std::min(B, std::max(1ll, std::min(h->cand_cap, leaf_ramp) / std::max(1ll, kcand)));
         }
         if (B < 1) B = 1;
+        if (sliced && !leaf && h->narrow && B <= kNarrowMax) {
+            // a handful of items: the single-block scheduler walks the levels on its own until the last
+            // level is reached, a chunk gets wide, or the search ends -- one round trip for all of it
+            Sched *hs = h->h_sched;
+            for (int l = 0; l < L; l++) {
+                hs->head[l] = h->head[l]; hs->tail[l] = h->tail[l]; hs->ptr[l] = h->level(l);
+                hs->fan[l] = fan[l]; hs->seen[l] = seen[l] ? 1 : 0;
+            }
+            hs->trees_left = h->prm.max_num_trees - seq_base;
+            hs->grow_calls = st.num_grow_calls; hs->max_grow_calls = h->prm.max_num_grow_calls;
+            hs->chunk_max = h->chunk_max; hs->cap = h->cap;
+            Sched *ds = static_cast<Sched *>(h->b_sched.p);
+            es ^= 1;
+            if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            h->ev_leaf[es] = false;
+            CK(cudaEventRecord(h->evk[es][0], h->stream));
+            CK(cudaMemcpyAsync(ds, hs, sizeof(Sched), cudaMemcpyHostToDevice, h->stream));
+            descend_kernel<SPL><<<1, kNarrowThreads, h->smem + (size_t)L * kMaxN, h->stream>>>(h->net, ds);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->evk[es][1], h->stream));
+            CK(cudaEventRecord(h->evk[es][2], h->stream));
+            h->evn[es] = 3;
+            CK(cudaMemcpyAsync(hs, ds, sizeof(Sched), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (int l = 0; l < L; l++) {
+                h->head[l] = hs->head[l]; h->tail[l] = hs->tail[l]; fan[l] = hs->fan[l]; seen[l] = hs->seen[l] != 0;
+            }
+            st.num_checks += hs->checks;
+            st.num_grow_calls = hs->grow_calls;
+            st.frontier_bytes += hs->frontier_bytes;
+            st.kernel_bytes[LICHEE_K_CHECK] += hs->check_bytes;
+            st.kernel_bytes[LICHEE_K_EMIT] += hs->emit_bytes;
+            st.num_launches++;
+            st.kernel_launches[LICHEE_K_CHECK]++;
+            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "narrow: %lld chunks, stop %d at level %d\n", hs->chunks, hs->stop, hs->stop_level);
+            if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
+            continue;
+        }
         const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
         if (ensure(h, h->b_mask, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_cnt, 4 * (size_t)B) != LICHEE_OK ||
             ensure(h, h->b_off, 4 * (size_t)B) != LICHEE_OK ||
@@ -1643,6 +1936,8 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_mask); give_back(h, h->b_cnt); give_back(h, h->b_off); give_back(h, h->b_tile);
     give_back(h, h->b_small);
     give_back(h, h->b_radix);
+    give_back(h, h->b_slab);
+    give_back(h, h->b_sched);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     if (h->stream) {
         DevCtx c;
@@ -1745,7 +2040,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
             CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
             for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
-            CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta)));
+            CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta) + sizeof(Sched)));
         }
     }
     const int Lp = std::max(1, h->L);
@@ -1817,8 +2112,22 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->cand_cap = std::max<long long>(h->cap, 1ll << 23);
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
+    {
+        // every level starts as a view of kNarrowCap items into one slab; a level that needs more gets
+        // its own buffer from the pool (ensure)
+        const size_t per = (size_t)kNarrowCap * h->stride;
+        CKE(ensure(h, h->b_slab, per * Lp));
+        for (int lv = 0; lv < Lp; lv++) {
+            h->b_level[lv].p = static_cast<char *>(h->b_slab.p) + per * lv;
+            h->b_level[lv].bytes = per;
+            h->b_level[lv].view = true;
+        }
+    }
     CKE(ensure(h, h->b_small, 256));
+    CKE(ensure(h, h->b_sched, sizeof(Sched)));
     h->h_meta = reinterpret_cast<TopMeta *>(h->h_scan + 1);
+    h->h_sched = reinterpret_cast<Sched *>(h->h_meta + 1);
+    h->narrow = getenv("LICHEE_NO_NARROW") == nullptr;
     for (int i = 0; i < 2; i++) {
         CKE(ensure(h, h->b_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
         CKE(ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * h->stride));
@@ -1839,6 +2148,8 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(descend_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx + kMaxN * kMaxN));
+        CKD(cudaFuncSetAttribute(descend_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx + kMaxN * kMaxN));
         CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 3 * kSelTile)));
         CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
         g_ctx.attrs_set[h->device] = true;
@@ -1904,7 +2215,7 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
     if (seq) *seq = h->h_top[k].seq;
     const uint8_t *b = h->h_tree.data() + (size_t)k * h->stride;
     // byte item_byte(t) holds the row index q of the parent of sigma[t]; q = 0 root, q = j+1 node sigma[j]
-    std::vector<int> par_of(h->L, 0);
+    int par_of[kMaxN];
     for (int t = 0; t < h->L; t++) {
         const int q = b[item_byte(t, h->stride >> 2)];
         if (q > h->L) { set_err("corrupt tree record: parent row %d at position %d", q, t); return LICHEE_ERR_STATE; }
@@ -1916,16 +2227,19 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
     }
     if (order) {
         // treeNodes: root first, then a preorder in which a node always follows its parent and the
-        // children of one parent keep the canonical (sigma) order used for the sums.
-        std::vector<std::vector<int>> ch(h->n);
-        for (int t = 0; t < h->L; t++) ch[par_of[t]].push_back(h->sigma[t]);
-        std::vector<int> stack{0};
-        int w = 0;
-        while (!stack.empty()) {
-            const int u = stack.back();
-            stack.pop_back();
+        // children of one parent keep the canonical (sigma) order used for the sums.  Children lists as
+        // CSR (counting sort by parent, stable in t), no allocation.
+        int first[kMaxN + 1], fill[kMaxN], kids[kMaxN], stack[kMaxN];
+        for (int u = 0; u <= h->n; u++) first[u] = 0;
+        for (int t = 0; t < h->L; t++) first[par_of[t] + 1]++;
+        for (int u = 0; u < h->n; u++) { first[u + 1] += first[u]; fill[u] = first[u]; }
+        for (int t = 0; t < h->L; t++) kids[fill[par_of[t]]++] = h->sigma[t];
+        int sp = 0, w = 0;
+        stack[sp++] = 0;
+        while (sp > 0 && w < h->n) {
+            const int u = stack[--sp];
             order[w++] = u;
-            for (auto it = ch[u].rbegin(); it != ch[u].rend(); ++it) stack.push_back(*it);
+            for (int i = first[u + 1] - 1; i >= first[u] && sp < kMaxN; i--) stack[sp++] = kids[i];
         }
         for (; w < h->n; w++) order[w] = -1;
     }
