@@ -850,13 +850,19 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     unsigned long long my_valid = 0;
 
     // A warp walks a contiguous run of items.  Neighbours in the canonical order differ in very few
-    // parent bytes (usually one), so after the first item of a run only the rows of the parents that
-    // gained or lost a child are recomputed; every other E, E' and pass bit carries over unchanged.
-    // Rows: E[q] = excess of parent q without the last node, F[q] = with it (passing candidates).
+    // parent bytes, and most of the time only in the LAST assigned one: the children of one item of the
+    // level above are adjacent and differ in where its node v (tree position L-2) hangs.  The state is
+    // therefore kept for the BASE item (the item with v taken out): per parent row q the excess E[q]
+    // without the last node and F[q] with it (passing candidates), presence and pass masks.  They carry
+    // over in registers and only the rows named by a changed base byte are recomputed.  On top of the base,
+    // ONE row per item is evaluated with v in place: the parent p that v hangs under (v is the highest
+    // position, hence the last child in p's sum -- same additions as a full evaluation of the item).
     // Lane l keeps rows l, l+32, l+64, l+96.  passq = passing candidates by row.
     double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};   // pb: pass bits by candidate index
-    unsigned w_prev = 0;
+    unsigned wb_prev = 0;
+    const bool has_v = level >= 1;                          // a tree position L-2 exists
+    const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     // runs are handed out from a counter, so a warp that drew cheap runs simply draws more of them
     for (;;) {
     long long run0 = 0;
@@ -869,31 +875,36 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         const unsigned w = w_next;
         // the next item's bytes are requested now so that their latency hides behind this item's work
         if (it + 1 < run1 && lane < wstride) w_next = __ldg(items + (it + 1) * wstride + lane);
-        unsigned todo[4];                                    // rows to (re)compute for this item
+        // base item: v unassigned
+        const unsigned wb = (has_v && lane == wl2) ? (w | (0xffu << sh2)) : w;
+        unsigned todo[4] = {0, 0, 0, 0};                     // base rows to (re)compute for this item
         bool fresh = it == run0;
         if (!fresh) {
-            // rows named by a byte that changed, in the old or the new item
-            unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            const unsigned diff = w ^ w_prev;
-            for (int r = 0; r <= rmax; r++) {
-                if ((diff >> (8 * r)) & 0xffu) {
-                    const unsigned bo = (w_prev >> (8 * r)) & 0xffu, bn = (w >> (8 * r)) & 0xffu;
-                    const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
-                    c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
-                    c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
-                    c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
-                    c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+            const unsigned diff = wb ^ wb_prev;
+            if (__any_sync(kFull, diff != 0)) {
+                // rows named by a base byte that changed, in the old or the new item
+                unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                for (int r = 0; r <= rmax; r++) {
+                    if ((diff >> (8 * r)) & 0xffu) {
+                        const unsigned bo = (wb_prev >> (8 * r)) & 0xffu, bn = (wb >> (8 * r)) & 0xffu;
+                        const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
+                        c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
+                        c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
+                        c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
+                        c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+                    }
                 }
+                todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
+                todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
+                if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
             }
-            todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
-            todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
-            if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
         }
-        w_prev = w;
+        wb_prev = wb;
         if (fresh) {
-            parent_presence(w, rmax, um);
+            parent_presence(wb, rmax, um);
             pb[0] = pb[1] = pb[2] = pb[3] = 0;
         }
+        if (fresh || (todo[0] | todo[1] | todo[2] | todo[3])) {
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             unsigned rows;
@@ -914,11 +925,11 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 double Eq = 0.0, Fq = 0.0;
                 bool pass = false;
                 if (!fresh) {                                // presence of a changed row: any byte equal to q
-                    const bool here = __ballot_sync(kFull, __vcmpeq4(w, q * 0x01010101u) != 0) != 0;
+                    const bool here = __ballot_sync(kFull, __vcmpeq4(wb, q * 0x01010101u) != 0) != 0;
                     um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
                 }
-                if ((um[g] >> bq) & 1u) {                   // parent present in the item
-                    pass = leaf_row<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1,
+                if ((um[g] >> bq) & 1u) {                   // parent present in the base item
+                    pass = leaf_row<SPL>(wb, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1,
                                          ((candq[g] >> bq) & 1u) != 0, Eq, Fq);
                 } else if (((candq[g] & okq[g]) >> bq) & 1u) {          // childless candidate: static
                     Fq = fstat_s[q];
@@ -935,6 +946,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 }
             }
         }
+        }
         // pass mask by candidate index (canonical order of the trees of this item): rows handled in the
         // loop above set their bit there; the static childless candidates of a fresh item are added here
         if (fresh) {
@@ -946,11 +958,36 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
             }
         }
+        // the one row that sees v: its parent p in this item
+        unsigned pbm0 = pb[0], pbm1 = pb[1], pbm2 = pb[2], pbm3 = pb[3];      // pass mask of the full item
+        unsigned pq0 = passq[0], pq1 = passq[1], pq2 = passq[2], pq3 = passq[3];
+        double E0 = E[0], E1 = E[1], E2 = E[2], E3 = E[3], F0 = F[0], F1 = F[1], F2 = F[2], F3 = F[3];
+        if (has_v) {
+            const unsigned p = (__shfl_sync(kFull, w, wl2) >> sh2) & 0xffu;
+            const unsigned gp = p >> 5, bp = p & 31;
+            const unsigned cq = gp == 0 ? candq[0] : gp == 1 ? candq[1] : gp == 2 ? candq[2] : candq[3];
+            const bool is_cand = ((cq >> bp) & 1u) != 0;
+            double Ep, Fp;
+            const bool pass = leaf_row<SPL>(w, p, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1, is_cand, Ep, Fp);
+            const bool mine = lane == (int)bp;
+            const unsigned bitq = 1u << bp;
+            if (gp == 0) { if (mine) { E0 = Ep; F0 = Fp; } pq0 = pass ? pq0 | bitq : pq0 & ~bitq; }
+            else if (gp == 1) { if (mine) { E1 = Ep; F1 = Fp; } pq1 = pass ? pq1 | bitq : pq1 & ~bitq; }
+            else if (gp == 2) { if (mine) { E2 = Ep; F2 = Fp; } pq2 = pass ? pq2 | bitq : pq2 & ~bitq; }
+            else { if (mine) { E3 = Ep; F3 = Fp; } pq3 = pass ? pq3 | bitq : pq3 & ~bitq; }
+            if (is_cand) {
+                const unsigned i = cidx_s[p], bit = 1u << (i & 31);
+                if ((i >> 5) == 0) pbm0 = pass ? pbm0 | bit : pbm0 & ~bit;
+                else if ((i >> 5) == 1) pbm1 = pass ? pbm1 | bit : pbm1 & ~bit;
+                else if ((i >> 5) == 2) pbm2 = pass ? pbm2 | bit : pbm2 & ~bit;
+                else pbm3 = pass ? pbm3 | bit : pbm3 & ~bit;
+            }
+        }
         {
-            const unsigned cnt = __popc(pb[0]) + __popc(pb[1]) + __popc(pb[2]) + __popc(pb[3]);
+            const unsigned cnt = __popc(pbm0) + __popc(pbm1) + __popc(pbm2) + __popc(pbm3);
             my_valid += cnt;
             if (lane == 0) {
-                mask_out[it] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                mask_out[it] = make_uint4(pbm0, pbm1, pbm2, pbm3);
                 count_out[it] = cnt;
             }
         }
@@ -958,7 +995,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         // Base reduction over the 128 slots, remembering what each lane received at every stage: a
         // tree differs from the base in one slot of one lane, so its total is that lane's partial
         // pushed through the same five additions -- bit-identical to a full butterfly.
-        const double P = __dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3]));
+        const double P = __dadd_rn(__dadd_rn(E0, E1), __dadd_rn(E2, E3));
         double rcv[5];
         {
             double v = P;
@@ -971,17 +1008,18 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             // this lane's partial with slot g swapped for F
-            const double A = g == 0 ? __dadd_rn(__dadd_rn(F[0], E[1]), __dadd_rn(E[2], E[3]))
-                           : g == 1 ? __dadd_rn(__dadd_rn(E[0], F[1]), __dadd_rn(E[2], E[3]))
-                           : g == 2 ? __dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(F[2], E[3]))
-                                    : __dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], F[3]));
+            const double A = g == 0 ? __dadd_rn(__dadd_rn(F0, E1), __dadd_rn(E2, E3))
+                           : g == 1 ? __dadd_rn(__dadd_rn(E0, F1), __dadd_rn(E2, E3))
+                           : g == 2 ? __dadd_rn(__dadd_rn(E0, E1), __dadd_rn(F2, E3))
+                                    : __dadd_rn(__dadd_rn(E0, E1), __dadd_rn(E2, F3));
+            const unsigned pqg = g == 0 ? pq0 : g == 1 ? pq1 : g == 2 ? pq2 : pq3;
             double x = A;
 #pragma unroll
             for (int st = 0; st < 5; st++) x = __dadd_rn(x, rcv[st]);
             // lane l now holds the total of the tree that hangs the last node under row g*32+l: every
             // tree of the item is evaluated at once, and only the few that may beat the threshold
             // go through the square root and the append
-            unsigned b = __ballot_sync(kFull, ((passq[g] >> lane) & 1u) && x <= tmax);
+            unsigned b = __ballot_sync(kFull, ((pqg >> lane) & 1u) && x <= tmax);
             while (b) {
                 const int bq = __ffs(b) - 1;
                 b &= b - 1;
