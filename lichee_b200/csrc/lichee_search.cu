@@ -79,6 +79,7 @@ struct DevNet {
     const uint4 *static_ok;  // [L]       bit i: candidate i passes the sum rule when it has no other child
     const double *leaf_static; // [128]   last level: excess E' of candidate i when the last node is its only child
     int n, S, SP, L, stride; // stride = bytes per frontier item (multiple of 16, <= 128)
+    int prune;               // every VAF >= 0: a partial tree's excess is a lower bound of every completion's
     double margin;
 };
 
@@ -104,6 +105,7 @@ struct TopMeta {             // device-resident state of the ranked list
     unsigned long long n_cand;  // candidates appended by the current leaf launch
     unsigned long long n_valid; // valid complete trees counted by the current leaf launch
     unsigned long long next_run; // work queue of the current leaf launch: next unclaimed run of items
+    unsigned long long n_bounded; // items of the current leaf launch whose trees were excluded by the lower bound
 };
 
 struct ScanOut {             // written by the scan, read back by the host once per chunk
@@ -776,7 +778,7 @@ __device__ __forceinline__ double parent_excess(double s0, double s1, double a0,
 template <int SPL>
 __device__ __noinline__ bool leaf_row(unsigned w, unsigned q, int rmax, int W, const double *vaf_s, int SP, int lane,
                                       double xv0, double xv1, double margin, bool valid0, bool valid1, bool is_cand,
-                                      double &Eq, double &Fq) {
+                                      bool want_f, double &Eq, double &Fq) {
     double s0, s1, a0, a1;
     child_sums<SPL>(w, q, rmax, W, vaf_s, SP, lane, s0, s1);
     load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
@@ -790,7 +792,7 @@ __device__ __noinline__ bool leaf_row(unsigned w, unsigned q, int rmax, int W, c
         bad |= valid1 && s1 > __dadd_rn(a1, margin);
     }
     if (__any_sync(kFull, bad)) return false;
-    Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
+    if (want_f) Fq = parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1);
     return true;
 }
 
@@ -848,6 +850,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         tmax = __dsqrt_rn(t) < tau ? t : -1.0;             // tau == 0: nothing can beat it
     }
     unsigned long long my_valid = 0;
+    unsigned my_bounded = 0;
 
     // A warp walks a contiguous run of items.  Neighbours in the canonical order differ in very few
     // parent bytes, and most of the time only in the LAST assigned one: the children of one item of the
@@ -861,6 +864,14 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};   // pb: pass bits by candidate index
     unsigned wb_prev = 0;
+    // Lower bound: VAFs are non-negative, so hanging further nodes under a parent never lowers its sum and
+    // (every operation of the fixed-shape reduction being monotone) never lowers a total.  The total of the
+    // BASE item's E rows therefore bounds the total of every tree below it; when it already exceeds what
+    // the full ranked list admits, the whole sibling group is only counted (sum-rule pass masks), not
+    // scored.  F rows are then filled in lazily: fstale marks rows whose F was skipped.
+    unsigned fstale[4] = {0, 0, 0, 0};
+    bool hopeless = false;
+    const bool prune = net.prune != 0 && full;
     const bool has_v = level >= 1;                          // a tree position L-2 exists
     const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     // runs are handed out from a counter, so a warp that drew cheap runs simply draws more of them
@@ -903,6 +914,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         if (fresh) {
             parent_presence(wb, rmax, um);
             pb[0] = pb[1] = pb[2] = pb[3] = 0;
+            fstale[0] = fstale[1] = fstale[2] = fstale[3] = 0;
         }
         if (fresh || (todo[0] | todo[1] | todo[2] | todo[3])) {
 #pragma unroll
@@ -928,9 +940,11 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                     const bool here = __ballot_sync(kFull, __vcmpeq4(wb, q * 0x01010101u) != 0) != 0;
                     um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
                 }
+                fstale[g] &= ~(1u << bq);
                 if ((um[g] >> bq) & 1u) {                   // parent present in the base item
                     pass = leaf_row<SPL>(wb, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1,
-                                         ((candq[g] >> bq) & 1u) != 0, Eq, Fq);
+                                         ((candq[g] >> bq) & 1u) != 0, !prune, Eq, Fq);
+                    if (prune && pass) fstale[g] |= 1u << bq;
                 } else if (((candq[g] & okq[g]) >> bq) & 1u) {          // childless candidate: static
                     Fq = fstat_s[q];
                     pass = true;
@@ -958,6 +972,51 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
             }
         }
+        if (prune && (fresh || (todo[0] | todo[1] | todo[2] | todo[3]))) {
+            // new base: its total bounds every tree of the sibling group from below
+            const double tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
+            hopeless = tb > tmax;
+        }
+        if (hopeless) {
+            // count only: the pass mask of the item is the base mask with the row of v's parent re-decided
+            unsigned m0 = pb[0], m1 = pb[1], m2 = pb[2], m3 = pb[3];
+            if (has_v) {
+                const unsigned p = (__shfl_sync(kFull, w, wl2) >> sh2) & 0xffu;
+                const unsigned gp = p >> 5, bp = p & 31;
+                const unsigned cq = gp == 0 ? candq[0] : gp == 1 ? candq[1] : gp == 2 ? candq[2] : candq[3];
+                if ((cq >> bp) & 1u) {
+                    const bool pass = row_passes<SPL>(w, p, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1);
+                    const unsigned i = cidx_s[p], bit = 1u << (i & 31);
+                    if ((i >> 5) == 0) m0 = pass ? m0 | bit : m0 & ~bit;
+                    else if ((i >> 5) == 1) m1 = pass ? m1 | bit : m1 & ~bit;
+                    else if ((i >> 5) == 2) m2 = pass ? m2 | bit : m2 & ~bit;
+                    else m3 = pass ? m3 | bit : m3 & ~bit;
+                }
+            }
+            const unsigned cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+            my_valid += cnt;
+            my_bounded++;
+            if (lane == 0) {
+                mask_out[it] = make_uint4(m0, m1, m2, m3);
+                count_out[it] = cnt;
+            }
+            continue;
+        }
+        if (fstale[0] | fstale[1] | fstale[2] | fstale[3]) {
+            // a group that may reach the list: fill in the F rows that were skipped
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                unsigned rows = fstale[g];
+                fstale[g] = 0;
+                while (rows) {
+                    const int bq = __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    double Eq, Fq;
+                    leaf_row<SPL>(wb, g * 32 + bq, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1, true, true, Eq, Fq);
+                    if (lane == bq) F[g] = Fq;
+                }
+            }
+        }
         // the one row that sees v: its parent p in this item
         unsigned pbm0 = pb[0], pbm1 = pb[1], pbm2 = pb[2], pbm3 = pb[3];      // pass mask of the full item
         unsigned pq0 = passq[0], pq1 = passq[1], pq2 = passq[2], pq3 = passq[3];
@@ -968,7 +1027,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             const unsigned cq = gp == 0 ? candq[0] : gp == 1 ? candq[1] : gp == 2 ? candq[2] : candq[3];
             const bool is_cand = ((cq >> bp) & 1u) != 0;
             double Ep, Fp;
-            const bool pass = leaf_row<SPL>(w, p, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1, is_cand, Ep, Fp);
+            const bool pass = leaf_row<SPL>(w, p, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1, is_cand, true, Ep, Fp);
             const bool mine = lane == (int)bp;
             const unsigned bitq = 1u << bp;
             if (gp == 0) { if (mine) { E0 = Ep; F0 = Fp; } pq0 = pass ? pq0 | bitq : pq0 & ~bitq; }
@@ -1045,6 +1104,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     }
     }
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
+    if (lane == 0 && my_bounded) atomicAdd(&meta->n_bounded, (unsigned long long)my_bounded);
 }
 
 // Gives every candidate its canonical sequence number (rank among the valid trees) now that the
@@ -1237,7 +1297,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
         meta->n_valid = 0;
-        meta->next_run = 0;
+        meta->next_run = 0; meta->n_bounded = 0;
     }
 }
 
@@ -1344,7 +1404,7 @@ radix_compact(const Cand *__restrict__ cands, long long m, RadixState *st, Cand 
     }
 }
 
-__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; }
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -1352,7 +1412,7 @@ __global__ void init_meta(TopMeta *meta) {
     meta->tau = INFINITY;
     meta->n_cand = 0;
     meta->n_valid = 0;
-    meta->next_run = 0;
+    meta->next_run = 0; meta->n_bounded = 0;
 }
 
 // unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
@@ -1846,7 +1906,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             }
             long long m = (long long)h->h_meta->n_cand;
             leaf_total = (long long)h->h_meta->n_valid;
-            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->tau, h->h_meta->count);
+            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld bounded=%llu tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->n_bounded, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
             if (m > 0) {
                 if (launch_scan(h, B, ~0ull >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
@@ -2177,6 +2237,11 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->net.ncand = reinterpret_cast<const uint8_t *>(nb + o_ncand);
     h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
     h->net.margin = params->vaf_error_margin;
+    {
+        bool nonneg = params->vaf_error_margin == params->vaf_error_margin;
+        for (size_t i = 0; i < (size_t)n * S; i++) if (!(vaf[i] >= 0.0) || !(vaf[i] <= 1e300)) nonneg = false;
+        h->net.prune = (nonneg && getenv("LICHEE_NO_PRUNE") == nullptr) ? 1 : 0;
+    }
     h->smem = (size_t)n * h->SP * sizeof(double) + kMaxN;
     h->smem_leaf = h->smem;
     if (h->device >= 0 && h->device < 64 && !g_ctx.attrs_set[h->device]) {
