@@ -81,6 +81,7 @@ struct DevNet {
     int n, S, SP, L, stride; // stride = bytes per frontier item (multiple of 16, <= 128)
     int prune;               // every VAF >= 0: a partial tree's excess is a lower bound of every completion's
     double margin;
+    uint4 static_both;       // level L-2, bit i: childless candidate i of node v also takes the last node u
 };
 
 // Frontier item layout: an item is W = stride/4 words; the parent (row index q) of tree position t
@@ -341,19 +342,27 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
 // kernels 2a-2c: exclusive scan of the pass counts (keeps the canonical order without atomics)
 // and the largest prefix of items whose children fit in the next level's buffer.
 // ------------------------------------------------------------------------------------------
+constexpr unsigned kCountMask = 0x3fffffffu;   // leaf-level counts carry two flag bits (kNewBase, kBounded)
+constexpr unsigned kNewBase = 0x80000000u;     // first child of its parent item
+constexpr unsigned kBounded = 0x40000000u;     // no tree below this item can enter the ranked list
+// what a scan adds up: the plain count, or (last level) the trees of the items that are not bounded, i.e.
+// an upper bound on the candidates a chunk can append
+__device__ __forceinline__ unsigned scan_value(unsigned x, int live_only) {
+    return (live_only && (x & kBounded)) ? 0u : x & kCountMask;
+}
 constexpr int kScanThreads = 256;
 constexpr int kScanPer = 8;
 constexpr int kScanTile = kScanThreads * kScanPer;
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_tiles(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned long long *tile_sum,
-           long long n) {
+           long long n, int live_only) {
     __shared__ unsigned warp_tot[kScanThreads / 32];
     const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanPer;
     unsigned v[kScanPer], run = 0;
 #pragma unroll
     for (int i = 0; i < kScanPer; i++) {
-        v[i] = base + i < n ? in[base + i] : 0;
+        v[i] = base + i < n ? scan_value(in[base + i], live_only) : 0;
         run += v[i];
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -393,7 +402,7 @@ __global__ void scan_tile_sums(unsigned long long *tile_sum, int n_tiles, ScanOu
 __global__ void __launch_bounds__(kScanThreads)
 scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
             const unsigned long long *__restrict__ tile_sum, long long n, unsigned long long limit,
-            ScanOut *out) {
+            ScanOut *out, int live_only) {
     const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanPer;
     const unsigned long long add = tile_sum[blockIdx.x];
     unsigned long long best = 0;
@@ -403,7 +412,7 @@ scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
         if (idx < n) {
             const unsigned long long ex = add + off[idx];
             off[idx] = (unsigned)ex;
-            const unsigned long long inc = ex + cnt[idx];
+            const unsigned long long inc = ex + scan_value(cnt[idx], live_only);
             if (inc <= limit) best = ((unsigned long long)(idx + 1) << 32) | inc;
         }
     }
@@ -417,7 +426,7 @@ constexpr long long kScanSingleMax = 4096;
 
 __global__ void __launch_bounds__(kScanSingleThreads)
 scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long long n, unsigned long long limit,
-            ScanOut *out) {
+            ScanOut *out, int live_only) {
     __shared__ unsigned warp_tot[kScanSingleThreads / 32];
     __shared__ unsigned long long best_s;
     if (threadIdx.x == 0) best_s = 0;
@@ -425,7 +434,7 @@ scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long l
     const long long lo = (long long)threadIdx.x * per;
     const long long hi = lo + per < n ? lo + per : n;
     unsigned run = 0;
-    for (long long i = lo; i < hi; i++) run += cnt[i];
+    for (long long i = lo; i < hi; i++) run += scan_value(cnt[i], live_only);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned inc = run;
 #pragma unroll
@@ -443,7 +452,7 @@ scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long l
     unsigned long long ex = woff + inc - run, best = 0;
     for (long long i = lo; i < hi; i++) {
         off[i] = (unsigned)ex;
-        ex += cnt[i];
+        ex += scan_value(cnt[i], live_only);
         if (ex <= limit) best = ((unsigned long long)(i + 1) << 32) | ex;
     }
     if (best) atomicMax(&best_s, best);
@@ -573,7 +582,7 @@ descend_kernel(DevNet net, Sched *sc) {
         int stop = -1;
         long long B = 0;
         if (lv < 0) stop = kStopDone;
-        else if (lv == L - 1) stop = kStopLeaf;
+        else if (lv >= L - 2) stop = kStopLeaf;        // the last two levels belong to check2 / emit2 / leaf
         else if (grow >= max_grow) stop = kStopGrow;
         else if (iter >= kNarrowIters) stop = kStopIters;
         else {
@@ -796,14 +805,277 @@ __device__ __noinline__ bool leaf_row(unsigned w, unsigned q, int rmax, int W, c
     return true;
 }
 
+// Largest total (sum of squared excesses) a tree may have and still enter the ranked list: a tree enters
+// a full list only with sqrt_rn(total) < tau.  sqrt_rn is monotone, so that is total <= tmax with tmax =
+// the largest double whose rounded square root is below tau: found by stepping a few ulps around
+// tau*tau.  No square root for rejected trees.  +inf while the list is not full.
+__device__ __forceinline__ double admit_bound(const TopMeta *meta, int num_save, bool &full, double &tau) {
+    tau = meta->tau;
+    full = meta->count >= (unsigned)num_save;
+    double tmax = INFINITY;
+    if (full) {
+        double t = __dmul_rn(tau, tau);
+        for (int i = 0; i < 8 && t > 0.0 && __dsqrt_rn(t) >= tau; i++) t = __longlong_as_double(__double_as_longlong(t) - 1);
+        for (int i = 0; i < 8 && __dsqrt_rn(__longlong_as_double(__double_as_longlong(t) + 1)) < tau; i++)
+            t = __longlong_as_double(__double_as_longlong(t) + 1);
+        tmax = __dsqrt_rn(t) < tau ? t : -1.0;             // tau == 0: nothing can beat it
+    }
+    return tmax;
+}
+
+__device__ __forceinline__ void put_bit(unsigned m[4], unsigned i, bool v) {
+    const unsigned bit = 1u << (i & 31), g = i >> 5;
+    m[0] = g == 0 ? (v ? m[0] | bit : m[0] & ~bit) : m[0];
+    m[1] = g == 1 ? (v ? m[1] | bit : m[1] & ~bit) : m[1];
+    m[2] = g == 2 ? (v ? m[2] | bit : m[2] & ~bit) : m[2];
+    m[3] = g == 3 ? (v ? m[3] | bit : m[3] & ~bit) : m[3];
+}
+__device__ __forceinline__ bool get_bit(const uint4 &m, unsigned i) {
+    const unsigned w = (i >> 5) == 0 ? m.x : (i >> 5) == 1 ? m.y : (i >> 5) == 2 ? m.z : m.w;
+    return ((w >> (i & 31)) & 1u) != 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels 1b / 3c: the level above the last one.  Its items are the BASES of the last level: the
+// children of one item differ only in where its node v hangs, and the last node u is then tried under
+// every candidate.  One pass over a parent row's children decides three things at once:
+//   bit 0  v fits under the row                    (the ordinary check of this level)
+//   bit 1  v and then u both fit under the row      (the only last-level decision that involves v)
+//   bit 2  u fits under the row without v           (the last-level decision for every other child)
+// so the pass mask of every last-level item is assembled by emit2_kernel with bit operations, and the
+// last-level kernel does arithmetic only for items that can still reach the ranked list: this kernel
+// also totals the excess of the base (fixed-shape reduction, same shape as the scoring) and flags the
+// base when that lower bound already exceeds what the full list admits.
+// ------------------------------------------------------------------------------------------
+template <int SPL>
+__device__ __noinline__ unsigned dual_row(unsigned w, unsigned q, int rmax, int W, const double *vaf_s, int SP, int lane,
+                                          double xv0, double xv1, double xu0, double xu1, double margin, bool valid0,
+                                          bool valid1, bool is_cv, bool is_cu, bool want_e, double &Eq) {
+    double s0, s1, a0, a1;
+    child_sums<SPL>(w, q, rmax, W, vaf_s, SP, lane, s0, s1);
+    load_row<SPL>(vaf_s, q, SP, lane, a0, a1);
+    Eq = want_e ? parent_excess<SPL>(s0, s1, a0, a1, valid0, valid1) : 0.0;
+    const double c0 = __dadd_rn(a0, margin), c1 = __dadd_rn(a1, margin);
+    unsigned r = 0;
+    if (is_cv) {
+        const double v0 = __dadd_rn(s0, xv0), v1 = __dadd_rn(s1, xv1);
+        bool bad = valid0 && v0 > c0;
+        if (SPL == 2) bad |= valid1 && v1 > c1;
+        if (!__any_sync(kFull, bad)) {
+            r |= 1u;
+            if (is_cu) {
+                bool bad2 = valid0 && __dadd_rn(v0, xu0) > c0;
+                if (SPL == 2) bad2 |= valid1 && __dadd_rn(v1, xu1) > c1;
+                if (!__any_sync(kFull, bad2)) r |= 2u;
+            }
+        }
+    }
+    if (is_cu) {
+        bool bad = valid0 && __dadd_rn(s0, xu0) > c0;
+        if (SPL == 2) bad |= valid1 && __dadd_rn(s1, xu1) > c1;
+        if (!__any_sync(kFull, bad)) r |= 4u;
+    }
+    return r;
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(kThreads, 2)
+check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, uint4 *__restrict__ mask_out,
+              unsigned *__restrict__ count_out, uint4 *__restrict__ both_out, uint4 *__restrict__ masku_out,
+              unsigned *__restrict__ flag_out, const TopMeta *meta, int num_save, int run_len) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vaf_s = reinterpret_cast<double *>(smem_raw);
+    uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    __shared__ uint8_t cidx_s[kMaxN], cidx2_s[kMaxN];     // by row: candidate index for v / for u
+    __shared__ unsigned candq_s[4], candq2_s[4];          // rows that are candidates of v / of u
+    const int level = net.L - 2;
+    const int k = net.ncand[level], k2 = net.ncand[level + 1];
+    if (threadIdx.x < 4) { candq_s[threadIdx.x] = 0; candq2_s[threadIdx.x] = 0; }
+    stage_network(net, level, vaf_s, cand_s);
+    if (threadIdx.x < k) {
+        const unsigned q = cand_s[threadIdx.x];
+        cidx_s[q] = (uint8_t)threadIdx.x;
+        atomicOr(&candq_s[q >> 5], 1u << (q & 31));
+    }
+    if (threadIdx.x < k2) {
+        const unsigned q = net.cand[(size_t)(level + 1) * kMaxN + threadIdx.x];
+        cidx2_s[q] = (uint8_t)threadIdx.x;
+        atomicOr(&candq2_s[q >> 5], 1u << (q & 31));
+    }
+    __syncthreads();
+    const unsigned candq[4] = {candq_s[0], candq_s[1], candq_s[2], candq_s[3]};
+    const unsigned candq2[4] = {candq2_s[0], candq2_s[1], candq2_s[2], candq2_s[3]};
+    const uint4 sokv = net.static_ok[level], soku = net.static_ok[level + 1], sboth = net.static_both;
+
+    const int lane = threadIdx.x & 31;
+    const int SP = net.SP;
+    const int wstride = net.stride >> 2;
+    const int rmax = level > 0 ? (level - 1) / wstride : -1;
+    double xv0, xv1, xu0, xu1;
+    load_row<SPL>(vaf_s, level + 1, SP, lane, xv0, xv1);
+    load_row<SPL>(vaf_s, level + 2, SP, lane, xu0, xu1);
+    const bool valid0 = lane < net.S;
+    const bool valid1 = SPL == 2 && lane + 32 < net.S;
+    bool full;
+    double tau;
+    const double tmax = admit_bound(meta, num_save, full, tau);
+    const bool prune = net.prune != 0 && full;
+    const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+
+    // per base item: bv = v fits (by v's candidate index), bb = v and u both fit (same index), bu = u fits
+    // without v (by u's candidate index), um = rows present, E = excess of the rows (lane l: rows l, l+32, ..)
+    unsigned bv[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0}, bu[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0};
+    double E[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned w_prev = 0;
+    for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len) {
+        const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
+        for (long long it = run0; it < run1; it++) {
+            const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+            bool fresh = it == run0;
+            unsigned todo[4] = {0, 0, 0, 0};
+            if (!fresh) {
+                unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                const unsigned diff = w ^ w_prev;
+                for (int r = 0; r <= rmax; r++) {
+                    if ((diff >> (8 * r)) & 0xffu) {
+                        const unsigned bo = (w_prev >> (8 * r)) & 0xffu, bn = (w >> (8 * r)) & 0xffu;
+                        const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
+                        c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
+                        c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
+                        c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
+                        c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+                    }
+                }
+                todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
+                todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
+                if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
+            }
+            w_prev = w;
+            if (fresh) {
+                parent_presence(w, rmax, um);
+                // every candidate starts childless (static answers); present rows overwrite theirs below
+                bv[0] = sokv.x; bv[1] = sokv.y; bv[2] = sokv.z; bv[3] = sokv.w;
+                bb[0] = sboth.x; bb[1] = sboth.y; bb[2] = sboth.z; bb[3] = sboth.w;
+                bu[0] = soku.x; bu[1] = soku.y; bu[2] = soku.z; bu[3] = soku.w;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                unsigned rows;
+                if (fresh) {
+                    E[g] = 0.0;
+                    rows = prune ? um[g] : um[g] & (candq[g] | candq2[g]);
+                } else {
+                    rows = todo[g];
+                }
+                while (rows) {
+                    const int bq = __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    const unsigned q = g * 32 + bq;
+                    if (!fresh) {
+                        const bool here = __ballot_sync(kFull, __vcmpeq4(w, q * 0x01010101u) != 0) != 0;
+                        um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
+                    }
+                    const bool is_cv = ((candq[g] >> bq) & 1u) != 0, is_cu = ((candq2[g] >> bq) & 1u) != 0;
+                    const unsigned iv = cidx_s[q], iu = cidx2_s[q];
+                    double Eq = 0.0;
+                    unsigned r;
+                    if ((um[g] >> bq) & 1u) {
+                        r = (prune || is_cv || is_cu)
+                                ? dual_row<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, xu0, xu1, net.margin, valid0,
+                                                valid1, is_cv, is_cu, prune, Eq)
+                                : 0u;
+                    } else {
+                        r = (is_cv && get_bit(sokv, iv) ? 1u : 0u) | (is_cv && get_bit(sboth, iv) ? 2u : 0u) |
+                            (is_cu && get_bit(soku, iu) ? 4u : 0u);
+                    }
+                    if (lane == bq) E[g] = Eq;
+                    if (is_cv) { put_bit(bv, iv, (r & 1u) != 0); put_bit(bb, iv, (r & 2u) != 0); }
+                    if (is_cu) put_bit(bu, iu, (r & 4u) != 0);
+                }
+            }
+            unsigned flag = 0;
+            if (prune) {
+                const double tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
+                flag = tb > tmax ? 1u : 0u;
+            }
+            if (lane == 0) {
+                mask_out[it] = make_uint4(bv[0], bv[1], bv[2], bv[3]);
+                count_out[it] = __popc(bv[0]) + __popc(bv[1]) + __popc(bv[2]) + __popc(bv[3]);
+                both_out[it] = make_uint4(bb[0], bb[1], bb[2], bb[3]);
+                masku_out[it] = make_uint4(bu[0], bu[1], bu[2], bu[3]);
+                flag_out[it] = flag;
+            }
+        }
+    }
+}
+
+// emit for the level above the last one: besides the child items it writes, for every child, the pass
+// mask of the last node u (the parent's "u without v" mask with the bit of v's parent replaced by the
+// "both" decision), its count, and the flags kNewBase (first child of its parent) / kBounded.
+__global__ void __launch_bounds__(kThreads)
+emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, const uint4 *__restrict__ mask,
+             const unsigned *__restrict__ off, const uint4 *__restrict__ both, const uint4 *__restrict__ masku,
+             const unsigned *__restrict__ flag, unsigned *__restrict__ out, uint4 *__restrict__ lmask_out,
+             unsigned *__restrict__ lcnt_out) {
+    __shared__ uint8_t cand_s[kMaxN], cidx2_s[kMaxN];
+    __shared__ unsigned candq2_s[4];
+    const int level = net.L - 2;
+    const int k2 = net.ncand[level + 1];
+    if (threadIdx.x < 4) candq2_s[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < kMaxN; i += blockDim.x) cand_s[i] = net.cand[(size_t)level * kMaxN + i];
+    __syncthreads();
+    if (threadIdx.x < k2) {
+        const unsigned q = net.cand[(size_t)(level + 1) * kMaxN + threadIdx.x];
+        cidx2_s[q] = (uint8_t)threadIdx.x;
+        atomicOr(&candq2_s[q >> 5], 1u << (q & 31));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wstride = net.stride >> 2;
+    const int wl = item_byte(level, wstride) >> 2, sh = 8 * (item_byte(level, wstride) & 3);
+    const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+    for (long long it = warp0; it < n_items; it += nwarps) {
+        const uint4 m4 = mask[it];
+        if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
+        const uint4 mb = both[it], mu = masku[it];
+        const unsigned fl = flag[it] ? kBounded : 0u;
+        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+        long long dst = (long long)off[it];
+        const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
+        unsigned first = kNewBase;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            unsigned b = mw[g];
+            while (b) {
+                const int i = g * 32 + __ffs(b) - 1;
+                b &= b - 1;
+                const unsigned q = cand_s[i];
+                unsigned cw = w;
+                if (lane == wl) cw = (w & ~(0xffu << sh)) | (q << sh);
+                if (lane < wstride) out[dst * wstride + lane] = cw;
+                if (lane == 0) {
+                    unsigned lm[4] = {mu.x, mu.y, mu.z, mu.w};
+                    if ((candq2_s[q >> 5] >> (q & 31)) & 1u) put_bit(lm, cidx2_s[q], get_bit(mb, (unsigned)i));
+                    lmask_out[dst] = make_uint4(lm[0], lm[1], lm[2], lm[3]);
+                    lcnt_out[dst] = (unsigned)(__popc(lm[0]) + __popc(lm[1]) + __popc(lm[2]) + __popc(lm[3])) | first | fl;
+                }
+                first = 0;
+                dst++;
+            }
+        }
+    }
+}
+
 // At the last level the sum-rule check and the scoring share all their sums, so one kernel does
 // both: it writes the pass mask + count of every item (for the scan that numbers the valid trees)
 // and appends the trees that beat the threshold with a provisional sequence number; seq_fixup_kernel
 // turns that into the canonical one once the scan has run.
 template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
-leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, long long item_base,
-            uint4 *__restrict__ mask_out, unsigned *__restrict__ count_out, int part, TopMeta *meta,
+leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__restrict__ fit, long long item_base,
+            const unsigned *__restrict__ lcnt, int part, TopMeta *meta,
             int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
@@ -836,21 +1108,14 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     const int rmax = level > 0 ? (level - 1) / wstride : -1;
     double xv0, xv1;
     load_row<SPL>(vaf_s, level + 1, SP, lane, xv0, xv1);
-    const double tau = meta->tau;
-    const bool full = meta->count >= (unsigned)num_save;
-    // A tree enters a full list only with sqrt_rn(total) < tau.  sqrt_rn is monotone, so that is
-    // total <= tmax with tmax = the largest double whose rounded square root is below tau: found
-    // once per thread by stepping a few ulps around tau*tau.  No square root for rejected trees.
-    double tmax = INFINITY;
-    if (full) {
-        double t = __dmul_rn(tau, tau);
-        for (int i = 0; i < 8 && t > 0.0 && __dsqrt_rn(t) >= tau; i++) t = __longlong_as_double(__double_as_longlong(t) - 1);
-        for (int i = 0; i < 8 && __dsqrt_rn(__longlong_as_double(__double_as_longlong(t) + 1)) < tau; i++)
-            t = __longlong_as_double(__double_as_longlong(t) + 1);
-        tmax = __dsqrt_rn(t) < tau ? t : -1.0;             // tau == 0: nothing can beat it
-    }
+    bool full;
+    double tau;
+    const double tmax = admit_bound(meta, num_save, full, tau);
     unsigned long long my_valid = 0;
     unsigned my_bounded = 0;
+    // the chunk: the longest prefix of the pending items whose unbounded trees fit the candidate buffer
+    // (scanned on the device just before this launch; the host reads the same number afterwards)
+    const long long n_items = (long long)(fit->fit >> 32);
 
     // A warp walks a contiguous run of items.  Neighbours in the canonical order differ in very few
     // parent bytes, and most of the time only in the LAST assigned one: the children of one item of the
@@ -862,7 +1127,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     // position, hence the last child in p's sum -- same additions as a full evaluation of the item).
     // Lane l keeps rows l, l+32, l+64, l+96.  passq = passing candidates by row.
     double E[4] = {0.0, 0.0, 0.0, 0.0}, F[4] = {0.0, 0.0, 0.0, 0.0};
-    unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};   // pb: pass bits by candidate index
+    unsigned passq[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0};
     unsigned wb_prev = 0;
     // Lower bound: VAFs are non-negative, so hanging further nodes under a parent never lowers its sum and
     // (every operation of the fixed-shape reduction being monotone) never lowers a total.  The total of the
@@ -874,22 +1139,45 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
     const bool prune = net.prune != 0 && full;
     const bool has_v = level >= 1;                          // a tree position L-2 exists
     const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
+    // The pass mask and the number of valid trees of every item were written by emit2_kernel together with
+    // the item (lcnt: count | kNewBase | kBounded), so items whose base was already out of reach when the
+    // level above was checked are skipped without being read.  State carries over between consecutively
+    // EVALUATED items only.
     // runs are handed out from a counter, so a warp that drew cheap runs simply draws more of them
+    long long last_it = -2;
     for (;;) {
     long long run0 = 0;
     if (lane == 0) run0 = (long long)atomicAdd(&meta->next_run, 1ull) * run_len;
     run0 = __shfl_sync(kFull, run0, 0);
     if (run0 >= n_items) break;
     const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
-    unsigned w_next = lane < wstride ? __ldg(items + run0 * wstride + lane) : 0xffffffffu;
-    for (long long it = run0; it < run1; it++) {
-        const unsigned w = w_next;
+    for (long long blk = run0; blk < run1; blk += 32) {
+    const long long idx = blk + lane;
+    const unsigned cw = idx < run1 ? __ldg(lcnt + idx) : kBounded;
+    if (idx < run1) my_valid += cw & kCountMask;
+    unsigned live = __ballot_sync(kFull, (cw & kBounded) == 0);
+    {
+        const int nblk = run1 - blk < 32 ? (int)(run1 - blk) : 32;
+        my_bounded += nblk - __popc(live);
+    }
+    unsigned w_next = 0;
+    long long next_it = -1;
+    while (live) {
+        const long long it = blk + __ffs(live) - 1;
+        live &= live - 1;
+        unsigned w;
+        if (next_it == it) w = w_next;
+        else w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
         // the next item's bytes are requested now so that their latency hides behind this item's work
-        if (it + 1 < run1 && lane < wstride) w_next = __ldg(items + (it + 1) * wstride + lane);
+        if (live) {
+            next_it = blk + __ffs(live) - 1;
+            w_next = lane < wstride ? __ldg(items + next_it * wstride + lane) : 0xffffffffu;
+        }
         // base item: v unassigned
         const unsigned wb = (has_v && lane == wl2) ? (w | (0xffu << sh2)) : w;
         unsigned todo[4] = {0, 0, 0, 0};                     // base rows to (re)compute for this item
-        bool fresh = it == run0;
+        bool fresh = it != last_it + 1;                      // no state from the item just before this one
+        last_it = it;
         if (!fresh) {
             const unsigned diff = wb ^ wb_prev;
             if (__any_sync(kFull, diff != 0)) {
@@ -913,7 +1201,6 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
         wb_prev = wb;
         if (fresh) {
             parent_presence(wb, rmax, um);
-            pb[0] = pb[1] = pb[2] = pb[3] = 0;
             fstale[0] = fstale[1] = fstale[2] = fstale[3] = 0;
         }
         if (fresh || (todo[0] | todo[1] | todo[2] | todo[3])) {
@@ -951,55 +1238,16 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
                 }
                 if (lane == bq) { E[g] = Eq; F[g] = Fq; }
                 passq[g] = pass ? passq[g] | (1u << bq) : passq[g] & ~(1u << bq);
-                if ((candq[g] >> bq) & 1u) {                 // same bit in the mask by candidate index
-                    const unsigned i = cidx_s[q], bit = 1u << (i & 31);
-                    pb[0] = (i >> 5) == 0 ? (pass ? pb[0] | bit : pb[0] & ~bit) : pb[0];
-                    pb[1] = (i >> 5) == 1 ? (pass ? pb[1] | bit : pb[1] & ~bit) : pb[1];
-                    pb[2] = (i >> 5) == 2 ? (pass ? pb[2] | bit : pb[2] & ~bit) : pb[2];
-                    pb[3] = (i >> 5) == 3 ? (pass ? pb[3] | bit : pb[3] & ~bit) : pb[3];
-                }
             }
         }
-        }
-        // pass mask by candidate index (canonical order of the trees of this item): rows handled in the
-        // loop above set their bit there; the static childless candidates of a fresh item are added here
-        if (fresh) {
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const unsigned absent = candq[g] & ~um[g] & okq[g];
-                const unsigned i = ((absent >> lane) & 1u) ? cidx_s[g * 32 + lane] : 0xffu;
-#pragma unroll
-                for (int gi = 0; gi < 4; gi++) pb[gi] |= __reduce_or_sync(kFull, (i >> 5) == (unsigned)gi ? 1u << (i & 31) : 0u);
-            }
         }
         if (prune && (fresh || (todo[0] | todo[1] | todo[2] | todo[3]))) {
             // new base: its total bounds every tree of the sibling group from below
             const double tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
             hopeless = tb > tmax;
         }
-        if (hopeless) {
-            // count only: the pass mask of the item is the base mask with the row of v's parent re-decided
-            unsigned m0 = pb[0], m1 = pb[1], m2 = pb[2], m3 = pb[3];
-            if (has_v) {
-                const unsigned p = (__shfl_sync(kFull, w, wl2) >> sh2) & 0xffu;
-                const unsigned gp = p >> 5, bp = p & 31;
-                const unsigned cq = gp == 0 ? candq[0] : gp == 1 ? candq[1] : gp == 2 ? candq[2] : candq[3];
-                if ((cq >> bp) & 1u) {
-                    const bool pass = row_passes<SPL>(w, p, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1);
-                    const unsigned i = cidx_s[p], bit = 1u << (i & 31);
-                    if ((i >> 5) == 0) m0 = pass ? m0 | bit : m0 & ~bit;
-                    else if ((i >> 5) == 1) m1 = pass ? m1 | bit : m1 & ~bit;
-                    else if ((i >> 5) == 2) m2 = pass ? m2 | bit : m2 & ~bit;
-                    else m3 = pass ? m3 | bit : m3 & ~bit;
-                }
-            }
-            const unsigned cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-            my_valid += cnt;
+        if (hopeless) {            // bounded by the current threshold (tighter than the one the level above saw)
             my_bounded++;
-            if (lane == 0) {
-                mask_out[it] = make_uint4(m0, m1, m2, m3);
-                count_out[it] = cnt;
-            }
             continue;
         }
         if (fstale[0] | fstale[1] | fstale[2] | fstale[3]) {
@@ -1018,7 +1266,6 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             }
         }
         // the one row that sees v: its parent p in this item
-        unsigned pbm0 = pb[0], pbm1 = pb[1], pbm2 = pb[2], pbm3 = pb[3];      // pass mask of the full item
         unsigned pq0 = passq[0], pq1 = passq[1], pq2 = passq[2], pq3 = passq[3];
         double E0 = E[0], E1 = E[1], E2 = E[2], E3 = E[3], F0 = F[0], F1 = F[1], F2 = F[2], F3 = F[3];
         if (has_v) {
@@ -1034,23 +1281,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             else if (gp == 1) { if (mine) { E1 = Ep; F1 = Fp; } pq1 = pass ? pq1 | bitq : pq1 & ~bitq; }
             else if (gp == 2) { if (mine) { E2 = Ep; F2 = Fp; } pq2 = pass ? pq2 | bitq : pq2 & ~bitq; }
             else { if (mine) { E3 = Ep; F3 = Fp; } pq3 = pass ? pq3 | bitq : pq3 & ~bitq; }
-            if (is_cand) {
-                const unsigned i = cidx_s[p], bit = 1u << (i & 31);
-                if ((i >> 5) == 0) pbm0 = pass ? pbm0 | bit : pbm0 & ~bit;
-                else if ((i >> 5) == 1) pbm1 = pass ? pbm1 | bit : pbm1 & ~bit;
-                else if ((i >> 5) == 2) pbm2 = pass ? pbm2 | bit : pbm2 & ~bit;
-                else pbm3 = pass ? pbm3 | bit : pbm3 & ~bit;
-            }
         }
-        {
-            const unsigned cnt = __popc(pbm0) + __popc(pbm1) + __popc(pbm2) + __popc(pbm3);
-            my_valid += cnt;
-            if (lane == 0) {
-                mask_out[it] = make_uint4(pbm0, pbm1, pbm2, pbm3);
-                count_out[it] = cnt;
-            }
-        }
-
         // Base reduction over the 128 slots, remembering what each lane received at every stage: a
         // tree differs from the base in one slot of one lane, so its total is that lane's partial
         // pushed through the same five additions -- bit-identical to a full butterfly.
@@ -1077,32 +1308,39 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, l
             for (int st = 0; st < 5; st++) x = __dadd_rn(x, rcv[st]);
             // lane l now holds the total of the tree that hangs the last node under row g*32+l: every
             // tree of the item is evaluated at once, and only the few that may beat the threshold
-            // go through the square root and the append
-            unsigned b = __ballot_sync(kFull, ((pqg >> lane) & 1u) && x <= tmax);
-            while (b) {
-                const int bq = __ffs(b) - 1;
-                b &= b - 1;
-                const double score = __dsqrt_rn(__shfl_sync(kFull, x, bq));
-                if (!full || score < tau) {
-                    if (lane == 0) {
-                        const unsigned long long slot = atomicAdd(&meta->n_cand, 1ull);
-                        if ((long long)slot < cand_cap) {
-                            const unsigned q = g * 32 + bq;
-                            Cand c;
-                            c.score = score;
-                            c.seq = 0;
-                            c.part = part;
+            // go through the square root and the append (one slot reservation per group, every lane
+            // writes its own tree)
+            const bool cand = ((pqg >> lane) & 1u) && x <= tmax;
+            const unsigned b = __ballot_sync(kFull, cand);
+            if (b) {
+                unsigned long long slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&meta->n_cand, (unsigned long long)__popc(b));
+                slot0 = __shfl_sync(kFull, slot0, 0);
+                if (cand) {
+                    const unsigned long long slot = slot0 + __popc(b & ((1u << lane) - 1u));
+                    if ((long long)slot < cand_cap) {
+                        const double score = __dsqrt_rn(x);
+                        const unsigned q = g * 32 + lane;
+                        Cand c;
+                        if (!full || score < tau) {
+                            c.score = score; c.seq = 0; c.part = part;
                             c.origin = (unsigned)(item_base + it);
                             c.pstar = q | ((unsigned)cidx_s[q] << 8);
                             c.pad = 0;
-                            cands[slot] = c;
+                        } else {            // rounded square root not below the threshold after all: an empty slot
+                            c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu;
+                            c.pstar = 0; c.pad = 1;
                         }
+                        cands[slot] = c;
                     }
                 }
             }
         }
     }
     }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_valid += __shfl_xor_sync(kFull, my_valid, d);
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
     if (lane == 0 && my_bounded) atomicAdd(&meta->n_bounded, (unsigned long long)my_bounded);
 }
@@ -1114,6 +1352,7 @@ __global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, 
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     Cand c = cands[t];
+    if (c.pad) return;
     const long long it = (long long)c.origin - item_base;
     const unsigned i = c.pstar >> 8;
     const uint4 m4 = mask[it];
@@ -1542,6 +1781,9 @@ struct lichee_search {
     long long cap = 0;                       // upper bound on items per level buffer
     long long cand_cap = 0;                  // upper bound on candidates one last-level launch may append
     DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_cands[2], b_top[2], b_tree[2];
+    DevBuf b_mask2, b_mask3, b_flag;         // level L-2 chunks: "v and u" mask, "u without v" mask, bounded flag
+    DevBuf b_lmask, b_lcnt;                  // last level, parallel to its item buffer: pass mask, count | flags
+    uint4 sok_last{};                        // static pass mask of the last node (n == 2: the only item's mask)
     DevBuf b_slab;                           // kNarrowCap items for every level (what the narrow scheduler emits into)
     DevBuf b_sched;                          // Sched, device copy
     ScanOut *h_scan = nullptr;               // pinned
@@ -1607,16 +1849,16 @@ int launch_check(lichee_search *h, int lv, const unsigned *items, long long n_it
     return LICHEE_OK;
 }
 
-int launch_scan(lichee_search *h, long long n_items, unsigned long long limit) {
+int launch_scan(lichee_search *h, const unsigned *cnt, long long n_items, unsigned long long limit, int live_only = 0) {
     if (n_items <= kScanSingleMax) {
-        scan_single<<<1, kScanSingleThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), n_items, limit, h->d_scan());
+        scan_single<<<1, kScanSingleThreads, 0, h->stream>>>(cnt, h->d_off(), n_items, limit, h->d_scan(), live_only);
         h->stats.num_launches += 1;
         h->stats.kernel_launches[LICHEE_K_SCAN] += 1;
     } else {
         const int tiles = (int)((n_items + kScanTile - 1) / kScanTile);
-        scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items);
+        scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(cnt, h->d_off(), h->d_tile(), n_items, live_only);
         scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile(), tiles, h->d_scan());
-        scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(h->d_cnt(), h->d_off(), h->d_tile(), n_items, limit, h->d_scan());
+        scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(cnt, h->d_off(), h->d_tile(), n_items, limit, h->d_scan(), live_only);
         h->stats.num_launches += 3;
         h->stats.kernel_launches[LICHEE_K_SCAN] += 3;
     }
@@ -1753,6 +1995,15 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     if (ensure(h, h->b_level[0], (size_t)h->stride) != LICHEE_OK) return LICHEE_ERR_CUDA;
     CK(cudaMemsetAsync(h->level(0), 0xff, h->stride, h->stream));
     h->tail[0] = 1;
+    if (L == 1) {
+        // two nodes: the only item is the empty one, its pass mask is the static mask of the last node
+        if (ensure(h, h->b_lmask, sizeof(uint4)) != LICHEE_OK || ensure(h, h->b_lcnt, 4) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        const uint4 m = h->sok_last;
+        const unsigned c = (unsigned)(__builtin_popcount(m.x) + __builtin_popcount(m.y) + __builtin_popcount(m.z) + __builtin_popcount(m.w)) | kNewBase;
+        CK(cudaMemcpyAsync(h->b_lmask.p, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->b_lcnt.p, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     CK(cudaEventRecord(h->ev0, h->stream));
 
     // fan[lv]: observed mean number of surviving children per item placed at level lv; yield[lv]
@@ -1767,7 +2018,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     float ms = 0;
     int es = 0;
     h->evn[0] = h->evn[1] = 0;
-    long long leaf_ramp = 1 << 15;           // candidates admitted per leaf launch while the threshold warms up
 
     for (;;) {
         int lv = -1;
@@ -1806,12 +2056,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         if (!leaf) {
             const long long guess = (long long)(0.8 * (double)h->cap / std::max(1.0, fan[lv]));
             B = std::min(B, std::max(1024ll, guess));
-        } else {
-            // every passing choice of the last node may become a candidate: keep them all
-            B = std::min(B, std::max(1ll, std::min(h->cand_cap, leaf_ramp) / std::max(1ll, kcand)));
         }
         if (B < 1) B = 1;
-        if (sliced && !leaf && h->narrow && B <= kNarrowMax) {
+        if (sliced && lv < L - 2 && h->narrow && B <= kNarrowMax) {
             // a handful of items: the single-block scheduler walks the levels on its own until the last
             // level is reached, a chunk gets wide, or the search ends -- one round trip for all of it
             Sched *hs = h->h_sched;
@@ -1850,6 +2097,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             continue;
         }
         const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
+        const bool dual = lv == L - 2;                       // the level whose children are the last-level items
+        if (dual && (ensure(h, h->b_mask2, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_mask3, sizeof(uint4) * (size_t)B) != LICHEE_OK ||
+                     ensure(h, h->b_flag, 4 * (size_t)B) != LICHEE_OK))
+            return LICHEE_ERR_CUDA;
         if (ensure(h, h->b_mask, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_cnt, 4 * (size_t)B) != LICHEE_OK ||
             ensure(h, h->b_off, 4 * (size_t)B) != LICHEE_OK ||
             ensure(h, h->b_tile, 8 * (size_t)(B / kScanTile + 2)) != LICHEE_OK)
@@ -1858,32 +2109,43 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;   // the chunk before last
         h->ev_leaf[es] = leaf;
         CK(cudaEventRecord(h->evk[es][0], h->stream));
-        const long long cand_cap = std::min(B * kcand, h->cand_cap);
-        if (!leaf) {
+        const long long cand_cap = h->cand_cap;
+        const unsigned *lcnt = static_cast<const unsigned *>(h->b_lcnt.p) + (leaf ? h->head[lv] : 0);
+        const uint4 *lmask = static_cast<const uint4 *>(h->b_lmask.p) + (leaf ? h->head[lv] : 0);
+        if (dual) {
+            const int grid = grid_for(B);
+            const int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
+            check2_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(
+                h->net, items, B, h->d_mask(), h->d_cnt(), static_cast<uint4 *>(h->b_mask2.p), static_cast<uint4 *>(h->b_mask3.p),
+                static_cast<unsigned *>(h->b_flag.p), h->d_meta(), h->prm.num_save, run_len);
+            CK(cudaGetLastError());
+            st.kernel_launches[LICHEE_K_CHECK]++;
+            st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 56);
+        } else if (!leaf) {
             if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_launches[LICHEE_K_CHECK]++;
             st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 20);
         } else {
-            // last level: check and scoring fused
+            // last level: scoring of the items that can still reach the ranked list.  Every unbounded tree of
+            // the chunk may become a candidate, so the chunk is the longest prefix of the pending items whose
+            // unbounded trees fit the candidate buffer: scanned on the device, read by the kernel from
+            // device memory and by the host afterwards (no round trip in between, no overflow possible).
             if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
-            // contiguous runs of items per warp (incremental evaluation): long enough to amortise the
-            // first full item, short enough to keep every warp slot of the grid busy
+            if (launch_scan(h, lcnt, B, (unsigned long long)cand_cap, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             const int grid = grid_for(B);
-            // several runs per warp (load balance between cheap and expensive runs), each 16..64 items long
-            // (measured: run lengths 16..36 perform alike once runs are claimed dynamically, longer ones
-            //  lose to the tail; chunks that stay L2-resident beat larger ones -- profiles/README.md)
-            int run_len = (int)std::min<long long>(32, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
-            if (run_len > B) run_len = (int)std::max<long long>(1, B);
+            // runs of items are claimed dynamically by the warps, in 32-item blocks (a bounded item costs a
+            // few instructions, an evaluated one hundreds)
+            int run_len = (int)std::min<long long>(256, std::max<long long>(32, (B / ((long long)grid * kWarpsPerBlock * 4) + 31) / 32 * 32));
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
-                h->net, items, B, h->head[lv], h->d_mask(), h->d_cnt(), R, h->d_meta(), h->prm.num_save,
+                h->net, items, h->d_scan(), h->head[lv], lcnt, R, h->d_meta(), h->prm.num_save,
                 h->d_cands(0), cand_cap, run_len);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_LEAF]++;
-            st.kernel_bytes[LICHEE_K_LEAF] += B * (long long)(h->stride + 20);
         }
         CK(cudaEventRecord(h->evk[es][1], h->stream));
         if (!leaf) {
-            if (launch_scan(h, B, (unsigned long long)h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            if (launch_scan(h, h->d_cnt(), B, (unsigned long long)h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
         }
         CK(cudaEventRecord(h->evk[es][2], h->stream));
@@ -1895,25 +2157,24 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // some of them beat the threshold (most chunks: none)
             CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
-            if (h->h_meta->n_cand > (unsigned long long)cand_cap) {
-                // more survivors than the candidate buffer holds (the threshold was stale for a whole
-                // region): nothing was consumed yet, so shrink the chunk and run it again
-                reset_n_cand<<<1, 1, 0, h->stream>>>(h->d_meta());
-                st.num_launches++;
-                leaf_ramp = std::max<long long>(kcand, std::min(leaf_ramp, B * kcand) / 4);
-                h->evn[es] = 0;
-                continue;
+            B = (long long)(h->h_scan->fit >> 32);           // the prefix the kernel took
+            if (B < 1 || h->h_meta->n_cand > (unsigned long long)cand_cap) {
+                set_err("last-level chunk accounting broken: %lld items, %llu candidates for %lld slots", B,
+                        (unsigned long long)h->h_meta->n_cand, cand_cap);
+                return LICHEE_ERR_STATE;
             }
             long long m = (long long)h->h_meta->n_cand;
             leaf_total = (long long)h->h_meta->n_valid;
             if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld bounded=%llu tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->n_bounded, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
+            // algorithmic bytes of the launch: the count word of every item, the item itself where it was evaluated
+            st.kernel_bytes[LICHEE_K_LEAF] += B * 4ll + (B - (long long)h->h_meta->n_bounded) * (long long)h->stride;
             if (m > 0) {
-                if (launch_scan(h, B, ~0ull >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (launch_scan(h, lcnt, B, ~0ull >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             }
             if (m > 0) {
-                seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], h->d_mask(),
+                seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], lmask,
                                                                              h->d_off(), seq_base, h->prm.max_num_trees);
                 CK(cudaGetLastError());
                 st.num_launches++;
@@ -1929,8 +2190,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             }
             CK(cudaEventRecord(h->evk[es][4], h->stream));
             h->evn[es] = 5;
-            // widen the next leaf launch once the threshold rejects most trees
-            if ((long long)h->h_meta->n_cand * 8 < leaf_ramp) leaf_ramp = std::min(leaf_ramp * 4, h->cand_cap);
             const long long total = leaf_total;
             st.num_checks += B * kcand;
             st.num_grow_calls += total;
@@ -1951,8 +2210,18 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             }
             if (total_fit > 0) {
                 if (ensure(h, h->b_level[lv + 1], (size_t)total_fit * h->stride) != LICHEE_OK) return LICHEE_ERR_CUDA;
-                emit_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(h->net, lv, items, n_fit, h->d_mask(),
-                                                                        h->d_off(), h->level(lv + 1));
+                if (dual) {
+                    if (ensure(h, h->b_lmask, sizeof(uint4) * (size_t)total_fit) != LICHEE_OK || ensure(h, h->b_lcnt, 4 * (size_t)total_fit) != LICHEE_OK)
+                        return LICHEE_ERR_CUDA;
+                    emit2_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(
+                        h->net, items, n_fit, h->d_mask(), h->d_off(), static_cast<const uint4 *>(h->b_mask2.p),
+                        static_cast<const uint4 *>(h->b_mask3.p), static_cast<const unsigned *>(h->b_flag.p), h->level(lv + 1),
+                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p));
+                    st.kernel_bytes[LICHEE_K_EMIT] += n_fit * 36ll + total_fit * 20ll;
+                } else {
+                    emit_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(h->net, lv, items, n_fit, h->d_mask(),
+                                                                            h->d_off(), h->level(lv + 1));
+                }
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(h->evk[es][3], h->stream));
                 h->evn[es] = 4;
@@ -2036,6 +2305,8 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_radix);
     give_back(h, h->b_slab);
     give_back(h, h->b_sched);
+    give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag);
+    give_back(h, h->b_lmask); give_back(h, h->b_lcnt);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     if (h->stream) {
         DevCtx c;
@@ -2169,6 +2440,26 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         }
         sok[t] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
     }
+    // level L-2, candidate i of node v without other children: do v and then the last node u both fit?
+    // (0.0 + VAF(v)) + VAF(u) against VAF(p) + margin, the same doubles as dual_row
+    uint4 sboth = make_uint4(0, 0, 0, 0);
+    if (h->L >= 2) {
+        const int t = h->L - 2, v = h->sigma[t], u = h->sigma[t + 1];
+        unsigned bits[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i < h->cands[t].size(); i++) {
+            const int p = h->cands[t][i];
+            bool ok = true;
+            for (int s = 0; s < S; s++) {
+                volatile double sv = 0.0 + vaf[(size_t)v * S + s];
+                volatile double svu = sv + vaf[(size_t)u * S + s];
+                volatile double capv = vaf[(size_t)p * S + s] + params->vaf_error_margin;
+                if (svu > capv) ok = false;
+            }
+            if (ok) bits[i >> 5] |= 1u << (i & 31);
+        }
+        sboth = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+    }
+    if (h->L >= 1) h->sok_last = sok[h->L - 1];
     // last level, candidate whose only child is the last node: its excess E' through the device's
     // fixed-shape reduction (lane value t[l] + t[l+32], xor-butterfly over 32 lanes), same IEEE operations
     std::vector<double> lstat(kMaxN, 0.0);
@@ -2237,6 +2528,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->net.ncand = reinterpret_cast<const uint8_t *>(nb + o_ncand);
     h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
     h->net.margin = params->vaf_error_margin;
+    h->net.static_both = sboth;
     {
         bool nonneg = params->vaf_error_margin == params->vaf_error_margin;
         for (size_t i = 0; i < (size_t)n * S; i++) if (!(vaf[i] >= 0.0) || !(vaf[i] <= 1e300)) nonneg = false;
@@ -2251,6 +2543,8 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         CKD(cudaFuncSetAttribute(check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CKD(cudaFuncSetAttribute(leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CKD(cudaFuncSetAttribute(leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(check2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CKD(cudaFuncSetAttribute(check2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         CKD(cudaFuncSetAttribute(descend_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx + kMaxN * kMaxN));
         CKD(cudaFuncSetAttribute(descend_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx + kMaxN * kMaxN));
         CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 3 * kSelTile)));
