@@ -45,6 +45,7 @@ constexpr int kWarpsPerBlock = 16;                 // 512 threads share one copy
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxN = LICHEE_MAX_NODES;
 constexpr int kMaxIncremental = 12;                // more changed parent rows than this: recompute the item
+constexpr int kCandBatch = 256;                    // candidate slots a warp reserves at a time
 constexpr int kSelThreads = 1024;
 constexpr int kSelTile = 1024;
 constexpr unsigned kFull = 0xffffffffu;
@@ -386,14 +387,23 @@ scan_tiles(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned
 }
 
 __global__ void scan_tile_sums(unsigned long long *tile_sum, int n_tiles, ScanOut *out) {
-    // single thread block, serial over tiles: n_tiles <= a few thousand
-    if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int i = 0; i < n_tiles; i++) {
-            unsigned long long t = tile_sum[i];
-            tile_sum[i] = run;
-            run += t;
+    // one warp: exclusive scan of the tile totals, 32 at a time
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x >= 32) return;
+    unsigned long long run = 0;
+    for (int base = 0; base < n_tiles; base += 32) {
+        const int i = base + lane;
+        const unsigned long long t = i < n_tiles ? tile_sum[i] : 0ull;
+        unsigned long long inc = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += u;
         }
+        if (i < n_tiles) tile_sum[i] = run + inc - t;
+        run += __shfl_sync(kFull, inc, 31);
+    }
+    if (lane == 0) {
         out->total = run;
         out->fit = 0;
     }
@@ -416,7 +426,19 @@ scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
             if (inc <= limit) best = ((unsigned long long)(idx + 1) << 32) | inc;
         }
     }
-    if (best) atomicMax(&out->fit, best);
+    // one atomic per block (every thread hitting the same word made this the slowest part of the scan)
+    __shared__ unsigned long long wbest[kScanThreads / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(kFull, best, d);
+        best = o > best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kScanThreads / 32; i++) best = wbest[i] > best ? wbest[i] : best;
+        if (best) atomicMax(&out->fit, best);
+    }
 }
 
 // Single-launch variant for narrow chunks (the first descent, small networks): one block, each
@@ -1113,6 +1135,16 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     const double tmax = admit_bound(meta, num_save, full, tau);
     unsigned long long my_valid = 0;
     unsigned my_bounded = 0;
+    // candidate slots are reserved kCandBatch at a time per warp (one atomic on the shared counter per batch,
+    // not per tree: in a good region millions of trees beat a stale threshold within one launch); slots a
+    // warp does not use are written as empty entries (pad = 1), which every consumer skips
+    unsigned long long res_next = 0, res_end = 0;
+    auto fill_empty = [&](unsigned long long from, unsigned long long to) {
+        Cand e;
+        e.score = INFINITY; e.seq = 0x7fffffffffffffffll; e.part = 0x7fffffff; e.origin = 0xffffffffu; e.pstar = 0; e.pad = 1;
+        for (unsigned long long sl = from + lane; sl < to; sl += 32)
+            if ((long long)sl < cand_cap) cands[sl] = e;
+    };
     // the chunk: the longest prefix of the pending items whose unbounded trees fit the candidate buffer
     // (scanned on the device just before this launch; the host reads the same number afterwards)
     const long long n_items = (long long)(fit->fit >> 32);
@@ -1313,11 +1345,16 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
             const bool cand = ((pqg >> lane) & 1u) && x <= tmax;
             const unsigned b = __ballot_sync(kFull, cand);
             if (b) {
-                unsigned long long slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&meta->n_cand, (unsigned long long)__popc(b));
-                slot0 = __shfl_sync(kFull, slot0, 0);
+                const unsigned c_n = __popc(b);
+                if (res_end - res_next < c_n) {
+                    fill_empty(res_next, res_end);
+                    unsigned long long r0 = 0;
+                    if (lane == 0) r0 = atomicAdd(&meta->n_cand, (unsigned long long)kCandBatch);
+                    res_next = __shfl_sync(kFull, r0, 0);
+                    res_end = res_next + kCandBatch;
+                }
                 if (cand) {
-                    const unsigned long long slot = slot0 + __popc(b & ((1u << lane) - 1u));
+                    const unsigned long long slot = res_next + __popc(b & ((1u << lane) - 1u));
                     if ((long long)slot < cand_cap) {
                         const double score = __dsqrt_rn(x);
                         const unsigned q = g * 32 + lane;
@@ -1334,11 +1371,13 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
                         cands[slot] = c;
                     }
                 }
+                res_next += c_n;
             }
         }
     }
     }
     }
+    fill_empty(res_next, res_end);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) my_valid += __shfl_xor_sync(kFull, my_valid, d);
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
@@ -2113,8 +2152,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         const unsigned *lcnt = static_cast<const unsigned *>(h->b_lcnt.p) + (leaf ? h->head[lv] : 0);
         const uint4 *lmask = static_cast<const uint4 *>(h->b_lmask.p) + (leaf ? h->head[lv] : 0);
         if (dual) {
-            const int grid = grid_for(B);
-            const int run_len = (int)std::min<long long>(64, std::max<long long>(1, B / ((long long)grid * kWarpsPerBlock)));
+            // the first item of a run is evaluated in full (every present row, with its excess), so runs are
+            // at least 32 items long even if that leaves part of the grid idle
+            const int run_len = (int)std::min<long long>(64, std::max<long long>(32, B / (148ll * 2 * kWarpsPerBlock)));
+            const int grid = (int)std::min<long long>(148 * 2, (B + (long long)run_len * kWarpsPerBlock - 1) / ((long long)run_len * kWarpsPerBlock));
             check2_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(
                 h->net, items, B, h->d_mask(), h->d_cnt(), static_cast<uint4 *>(h->b_mask2.p), static_cast<uint4 *>(h->b_mask3.p),
                 static_cast<unsigned *>(h->b_flag.p), h->d_meta(), h->prm.num_save, run_len);
@@ -2131,7 +2172,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // unbounded trees fit the candidate buffer: scanned on the device, read by the kernel from
             // device memory and by the host afterwards (no round trip in between, no overflow possible).
             if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
-            if (launch_scan(h, lcnt, B, (unsigned long long)cand_cap, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            // (slots are reserved in batches: up to 31 of every 256 and one batch per warp may stay empty)
+            const long long cand_limit = std::max<long long>(128, (cand_cap - (long long)kCandBatch * 148 * 3 * kWarpsPerBlock) / 5 * 4);
+            if (launch_scan(h, lcnt, B, (unsigned long long)cand_limit, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             const int grid = grid_for(B);
             // runs of items are claimed dynamically by the warps, in 32-item blocks (a bounded item costs a
@@ -2497,7 +2540,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     CKD(cudaMemcpyAsync(nb + o_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
-    h->chunk_max = std::min<long long>(h->cap, 1ll << 20);
+    h->chunk_max = std::min<long long>(h->cap, 1ll << 21);
     h->cand_cap = std::max<long long>(h->cap, 1ll << 23);
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
