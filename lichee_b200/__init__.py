@@ -131,20 +131,32 @@ class PHYTree:
     """Ranked spanning tree returned by the device (PHYTree.java:44-54).  treeNodes / treeEdges are
     rebuilt on first use from the parent and insertion-order arrays the ABI returns."""
 
-    def __init__(self, score, parent, order, seq):
-        self.errorScore = float(score)
-        self._parent = parent
-        self._order = order
-        self.seq = int(seq)
+    __slots__ = ("errorScore", "seq", "_par2d", "_ord2d", "_k", "_edges")
+
+    def __init__(self, score, parent, order, seq, k=None):
+        # parent / order: this tree's rows, or (k given) the whole ranked list's 2-D arrays, sliced on first use
+        self.errorScore = score
+        self.seq = seq
+        self._par2d = parent
+        self._ord2d = order
+        self._k = k
         self._edges = None
 
     @property
+    def _parent(self):
+        return self._par2d if self._k is None else self._par2d[self._k]
+
+    @property
+    def _order(self):
+        return self._ord2d if self._k is None else self._ord2d[self._k]
+
+    @property
     def parent(self):
-        return [int(x) for x in self._parent]
+        return self._parent.tolist()
 
     @property
     def treeNodes(self):
-        return [int(x) for x in self._order if x >= 0]
+        return [x for x in self._order.tolist() if x >= 0]
 
     @property
     def treeEdges(self):
@@ -227,7 +239,7 @@ class LineageSearch:
         order = np.zeros(self.n, dtype=np.int32)
         _ck(lib().lichee_search_get_tree(self._h, k, ctypes.byref(score), par.ctypes.data, order.ctypes.data,
                                          ctypes.byref(seq)))
-        return PHYTree(score.value, par, order, seq.value)
+        return PHYTree(float(score.value), par, order, int(seq.value))
 
     def trees(self):
         m = int(self.stats().num_saved)
@@ -239,7 +251,7 @@ class LineageSearch:
         seq = np.zeros(m, dtype=np.int64)
         _ck(lib().lichee_search_get_trees(self._h, 0, m, sc.ctypes.data, par.ctypes.data, order.ctypes.data,
                                           seq.ctypes.data))
-        return [PHYTree(*t) for t in zip(sc.tolist(), par, order, seq.tolist())]
+        return [PHYTree(s_, par, order, q_, k) for k, (s_, q_) in enumerate(zip(sc.tolist(), seq.tolist()))]
 
     def record_bytes(self):
         return int(lib().lichee_record_bytes(self._h))

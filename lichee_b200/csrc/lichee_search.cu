@@ -2058,6 +2058,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     int es = 0;
     h->evn[0] = h->evn[1] = 0;
 
+    bool list_full = false;                  // the ranked list held num_save trees at the last read-back
     for (;;) {
         int lv = -1;
         if (!sliced) {
@@ -2152,9 +2153,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         const unsigned *lcnt = static_cast<const unsigned *>(h->b_lcnt.p) + (leaf ? h->head[lv] : 0);
         const uint4 *lmask = static_cast<const uint4 *>(h->b_lmask.p) + (leaf ? h->head[lv] : 0);
         if (dual) {
-            // the first item of a run is evaluated in full (every present row, with its excess), so runs are
-            // at least 32 items long even if that leaves part of the grid idle
-            const int run_len = (int)std::min<long long>(64, std::max<long long>(32, B / (148ll * 2 * kWarpsPerBlock)));
+            // one run per warp, sized so that the grid is one full wave of two blocks per SM (the first item of a
+            // run is evaluated in full, every present row with its excess: runs shorter than 8 items do not pay)
+            const long long slots = 148ll * 2 * kWarpsPerBlock;
+            const int run_len = (int)std::min<long long>(64, std::max<long long>(8, (B + slots - 1) / slots));
             const int grid = (int)std::min<long long>(148 * 2, (B + (long long)run_len * kWarpsPerBlock - 1) / ((long long)run_len * kWarpsPerBlock));
             check2_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(
                 h->net, items, B, h->d_mask(), h->d_cnt(), static_cast<uint4 *>(h->b_mask2.p), static_cast<uint4 *>(h->b_mask3.p),
@@ -2173,7 +2175,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // device memory and by the host afterwards (no round trip in between, no overflow possible).
             if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
             // (slots are reserved in batches: up to 31 of every 256 and one batch per warp may stay empty)
-            const long long cand_limit = std::max<long long>(128, (cand_cap - (long long)kCandBatch * 148 * 3 * kWarpsPerBlock) / 5 * 4);
+            // (while the ranked list is still filling up every tree is a candidate, so the first chunk stays small,
+            //  yet large enough for a whole search under the reference's MAX_NUM_TREES = 100000)
+            long long cand_limit = std::max<long long>(128, (cand_cap - (long long)kCandBatch * 148 * 3 * kWarpsPerBlock) / 5 * 4);
+            if (!list_full) cand_limit = std::min<long long>(cand_limit, 1 << 17);
             if (launch_scan(h, lcnt, B, (unsigned long long)cand_limit, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             const int grid = grid_for(B);
@@ -2208,6 +2213,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             }
             long long m = (long long)h->h_meta->n_cand;
             leaf_total = (long long)h->h_meta->n_valid;
+            list_full = h->h_meta->count >= (unsigned)h->prm.num_save || m >= (long long)h->prm.num_save;
             if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld bounded=%llu tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->n_bounded, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
             // algorithmic bytes of the launch: the count word of every item, the item itself where it was evaluated

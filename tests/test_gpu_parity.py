@@ -363,3 +363,39 @@ def test_mid_size_tree_set_vs_reference_search(built, seed):
         assert abs(ref["scores"][k] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
         key = bytes(np.asarray(t.parent, dtype=np.int32))
         assert key in by_tree and abs(by_tree[key] - t.errorScore) <= REL * max(abs(t.errorScore), 1e-300)
+
+
+def test_scheduler_and_bound_do_not_change_results(built, monkeypatch):
+    """The single-block scheduler of narrow chunks (descend_kernel) and the lower bound that lets the last
+    two levels count whole sibling groups without scoring them can be switched off (LICHEE_NO_NARROW,
+    LICHEE_NO_PRUNE): tree counts, check counts, ranked trees, scores and sequence numbers must not move,
+    and the bound must actually have skipped work when it is on."""
+    cases = [make_instance(12, 5, seed=4), make_instance(30, 12, seed=7), make_instance(14, 40, seed=8)]
+    for net, prm in cases:
+        base = None
+        for env in ({}, {"LICHEE_NO_NARROW": "1"}, {"LICHEE_NO_PRUNE": "1"},
+                    {"LICHEE_NO_NARROW": "1", "LICHEE_NO_PRUNE": "1"}):
+            for k in ("LICHEE_NO_NARROW", "LICHEE_NO_PRUNE"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            st, trees, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 25, max_num_trees=2_000_000)
+            key = (st["num_trees"], [(t.errorScore, t.seq, t.parent) for t in trees])
+            if base is None:
+                base = key
+            else:
+                assert key == base, env
+    for k in ("LICHEE_NO_NARROW", "LICHEE_NO_PRUNE"):
+        monkeypatch.delenv(k, raising=False)
+
+
+def test_two_node_and_three_node_networks(built):
+    """The last two tree levels have their own kernels (check2 / emit2 / leaf): the smallest networks, where
+    those levels are the first ones, against the specification."""
+    # root + one node; root + two nodes in every edge configuration that keeps the root the only source
+    assert_matches_canonical([[1], []], np.array([[0.5, 0.5], [0.2, 0.3]]), 0.1, num_save=5)
+    vaf = np.array([[0.5, 0.5, 0.5], [0.3, 0.2, 0.25], [0.2, 0.2, 0.1]])
+    for adj in ([[1, 2], [], []], [[1, 2], [2], []], [[1], [2], []]):
+        assert_matches_canonical(adj, vaf, 0.1, num_save=5)
+    # nothing fits under anything but the root
+    assert_matches_canonical([[1, 2], [2], []], np.array([[0.5, 0.5], [0.4, 0.4], [0.45, 0.45]]), 0.0, num_save=3)
