@@ -113,6 +113,8 @@ struct TopMeta {             // device-resident state of the ranked list
 struct ScanOut {             // written by the scan, read back by the host once per chunk
     unsigned long long fit;  // (items that fit) << 32 | children they produce
     unsigned long long total;
+    unsigned long long live; // emit2_kernel: last-level items written that are not bounded (zeroed by the host)
+    unsigned long long trees; // emit2_kernel: valid complete trees below the items written
 };
 
 __device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b) {
@@ -343,8 +345,7 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
 // kernels 2a-2c: exclusive scan of the pass counts (keeps the canonical order without atomics)
 // and the largest prefix of items whose children fit in the next level's buffer.
 // ------------------------------------------------------------------------------------------
-constexpr unsigned kCountMask = 0x3fffffffu;   // leaf-level counts carry two flag bits (kNewBase, kBounded)
-constexpr unsigned kNewBase = 0x80000000u;     // first child of its parent item
+constexpr unsigned kCountMask = 0x3fffffffu;   // last-level counts carry a flag bit
 constexpr unsigned kBounded = 0x40000000u;     // no tree below this item can enter the ranked list
 // what a scan adds up: the plain count, or (last level) the trees of the items that are not bounded, i.e.
 // an upper bound on the candidates a chunk can append
@@ -1034,12 +1035,14 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
 
 // emit for the level above the last one: besides the child items it writes, for every child, the pass
 // mask of the last node u (the parent's "u without v" mask with the bit of v's parent replaced by the
-// "both" decision), its count, and the flags kNewBase (first child of its parent) / kBounded.
+// "both" decision) and its count.  Children of a BOUNDED parent get the count and the kBounded flag only:
+// nothing reads their bytes or masks, so they are not written (their slots in the level buffer stay
+// reserved, which keeps item indices and sequence numbers where they belong).
 __global__ void __launch_bounds__(kThreads)
 emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, const uint4 *__restrict__ mask,
              const unsigned *__restrict__ off, const uint4 *__restrict__ both, const uint4 *__restrict__ masku,
              const unsigned *__restrict__ flag, unsigned *__restrict__ out, uint4 *__restrict__ lmask_out,
-             unsigned *__restrict__ lcnt_out) {
+             unsigned *__restrict__ lcnt_out, ScanOut *so) {
     __shared__ uint8_t cand_s[kMaxN], cidx2_s[kMaxN];
     __shared__ unsigned candq2_s[4];
     const int level = net.L - 2;
@@ -1058,15 +1061,35 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
     const int wl = item_byte(level, wstride) >> 2, sh = 8 * (item_byte(level, wstride) & 3);
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+    unsigned long long my_trees = 0, my_live = 0;       // per lane, reduced at the end
     for (long long it = warp0; it < n_items; it += nwarps) {
         const uint4 m4 = mask[it];
         if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
         const uint4 mb = both[it], mu = masku[it];
         const unsigned fl = flag[it] ? kBounded : 0u;
-        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
         long long dst = (long long)off[it];
         const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
-        unsigned first = kNewBase;
+        if (fl) {
+            // bounded base: nobody will read its children, only their tree counts are needed (for the number
+            // of valid trees and the sequence numbers of later candidates).  One child per lane, no item bytes.
+            const unsigned n_u = __popc(mu.x) + __popc(mu.y) + __popc(mu.z) + __popc(mu.w);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const unsigned b = mw[g];
+                const unsigned pos = __fns(b, 0, lane + 1);          // lane-th set bit of the group
+                if (pos < 32u) {
+                    const unsigned i = g * 32 + pos, q = cand_s[i];
+                    unsigned cnt = n_u;
+                    if ((candq2_s[q >> 5] >> (q & 31)) & 1u)
+                        cnt = cnt - (get_bit(mu, cidx2_s[q]) ? 1u : 0u) + (get_bit(mb, i) ? 1u : 0u);
+                    lcnt_out[dst + lane] = cnt | fl;
+                    my_trees += cnt;
+                }
+                dst += __popc(b);
+            }
+            continue;
+        }
+        const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             unsigned b = mw[g];
@@ -1080,13 +1103,24 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
                 if (lane == 0) {
                     unsigned lm[4] = {mu.x, mu.y, mu.z, mu.w};
                     if ((candq2_s[q >> 5] >> (q & 31)) & 1u) put_bit(lm, cidx2_s[q], get_bit(mb, (unsigned)i));
+                    const unsigned cnt = __popc(lm[0]) + __popc(lm[1]) + __popc(lm[2]) + __popc(lm[3]);
                     lmask_out[dst] = make_uint4(lm[0], lm[1], lm[2], lm[3]);
-                    lcnt_out[dst] = (unsigned)(__popc(lm[0]) + __popc(lm[1]) + __popc(lm[2]) + __popc(lm[3])) | first | fl;
+                    lcnt_out[dst] = cnt;
+                    my_trees += cnt;
+                    my_live += 1;
                 }
-                first = 0;
                 dst++;
             }
         }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_trees += __shfl_xor_sync(kFull, my_trees, d);
+        my_live += __shfl_xor_sync(kFull, my_live, d);
+    }
+    if (lane == 0) {
+        if (my_trees) atomicAdd(&so->trees, my_trees);
+        if (my_live) atomicAdd(&so->live, my_live);
     }
 }
 
@@ -1172,7 +1206,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     const bool has_v = level >= 1;                          // a tree position L-2 exists
     const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     // The pass mask and the number of valid trees of every item were written by emit2_kernel together with
-    // the item (lcnt: count | kNewBase | kBounded), so items whose base was already out of reach when the
+    // the item (lcnt: count | kBounded), so items whose base was already out of reach when the
     // level above was checked are skipped without being read.  State carries over between consecutively
     // EVALUATED items only.
     // runs are handed out from a counter, so a warp that drew cheap runs simply draws more of them
@@ -2038,7 +2072,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         // two nodes: the only item is the empty one, its pass mask is the static mask of the last node
         if (ensure(h, h->b_lmask, sizeof(uint4)) != LICHEE_OK || ensure(h, h->b_lcnt, 4) != LICHEE_OK) return LICHEE_ERR_CUDA;
         const uint4 m = h->sok_last;
-        const unsigned c = (unsigned)(__builtin_popcount(m.x) + __builtin_popcount(m.y) + __builtin_popcount(m.z) + __builtin_popcount(m.w)) | kNewBase;
+        const unsigned c = (unsigned)(__builtin_popcount(m.x) + __builtin_popcount(m.y) + __builtin_popcount(m.z) + __builtin_popcount(m.w));
         CK(cudaMemcpyAsync(h->b_lmask.p, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->b_lcnt.p, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -2059,6 +2093,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     h->evn[0] = h->evn[1] = 0;
 
     bool list_full = false;                  // the ranked list held num_save trees at the last read-back
+    // what emit2_kernel reported about the current fill of the last level: items that are not bounded, valid
+    // trees below all of them (fill_items = 0: unknown, e.g. after the level was cut into slices)
+    long long fill_items = 0, fill_live = 0, fill_trees = 0, fill_parents = 0;
+    bool fill_pending = false;               // emit2's counters are still on their way to the host
     for (;;) {
         int lv = -1;
         if (!sliced) {
@@ -2098,6 +2136,32 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             B = std::min(B, std::max(1024ll, guess));
         }
         if (B < 1) B = 1;
+        if (leaf && fill_pending) {
+            CK(cudaStreamSynchronize(h->stream));
+            fill_pending = false;
+            fill_live = (long long)h->h_scan->live;
+            fill_trees = (long long)h->h_scan->trees;
+            // emit2's algorithmic bytes: masks, flag and offset of every parent, a count word per child, and
+            // item + mask for the children that are not bounded
+            st.kernel_bytes[LICHEE_K_EMIT] += fill_parents * 56ll + fill_items * 4ll + fill_live * (long long)(h->stride + 16);
+        }
+        if (leaf && fill_items > 0 && fill_live == 0 && B == pending && pending == fill_items) {
+            // no item of this fill can reach the ranked list: its trees are counted, nothing is launched
+            fill_items = 0;
+            st.num_checks += B * kcand;
+            st.num_grow_calls += fill_trees;
+            const long long before = seq_base;
+            seq_base += fill_trees;
+            st.num_scored += std::min(seq_base, (long long)h->prm.max_num_trees) - std::min(before, (long long)h->prm.max_num_trees);
+            fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * (double)fill_trees / (double)B : (double)fill_trees / (double)B;
+            seen[lv] = true;
+            h->head[lv] = h->tail[lv] = 0;
+            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf fill B=%lld counted only: %lld trees\n", B, fill_trees);
+            if (seq_base >= h->prm.max_num_trees) { st.status |= LICHEE_STATUS_TREE_CAP; break; }
+            if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
+            continue;
+        }
+        if (leaf) fill_items = 0;                 // a chunk of the fill goes through the kernels: totals no longer apply
         if (sliced && lv < L - 2 && h->narrow && B <= kNarrowMax) {
             // a handful of items: the single-block scheduler walks the levels on its own until the last
             // level is reached, a chunk gets wide, or the search ends -- one round trip for all of it
@@ -2262,11 +2326,15 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 if (dual) {
                     if (ensure(h, h->b_lmask, sizeof(uint4) * (size_t)total_fit) != LICHEE_OK || ensure(h, h->b_lcnt, 4 * (size_t)total_fit) != LICHEE_OK)
                         return LICHEE_ERR_CUDA;
+                    CK(cudaMemsetAsync(&h->d_scan()->live, 0, 2 * sizeof(unsigned long long), h->stream));
                     emit2_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(
                         h->net, items, n_fit, h->d_mask(), h->d_off(), static_cast<const uint4 *>(h->b_mask2.p),
                         static_cast<const uint4 *>(h->b_mask3.p), static_cast<const unsigned *>(h->b_flag.p), h->level(lv + 1),
-                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p));
-                    st.kernel_bytes[LICHEE_K_EMIT] += n_fit * 36ll + total_fit * 20ll;
+                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p), h->d_scan());
+                    CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
+                    fill_pending = true;                      // read at the next last-level chunk
+                    fill_items = total_fit;
+                    fill_parents = n_fit;
                 } else {
                     emit_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(h->net, lv, items, n_fit, h->d_mask(),
                                                                             h->d_off(), h->level(lv + 1));
@@ -2283,7 +2351,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             st.num_checks += n_fit * kcand;
             st.num_grow_calls += total_fit;
             st.frontier_bytes += (n_fit + total_fit) * (long long)h->stride;
-            st.kernel_bytes[LICHEE_K_EMIT] += n_fit * (long long)(h->stride + 20) + total_fit * (long long)h->stride;
+            if (!dual) st.kernel_bytes[LICHEE_K_EMIT] += n_fit * (long long)(h->stride + 20) + total_fit * (long long)h->stride;
             const double f = (double)total_fit / (double)n_fit;
             fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * f : f;
             seen[lv] = true;

@@ -21,7 +21,7 @@ while time.time() - t0 < budget:
         net, prm = make_instance(rng.randint(3, 60), rng.choice([2, 5, 12, 20, 33, 64]), rng.randint(0, 10**6),
                                  noise=rng.choice([0.0, 0.005, 0.02]), complete=rng.random() < 0.7)
         adj, vaf, margin = net.adj, np.array(net.aaf), rng.choice([0.02, 0.1])
-    cap = rng.choice([1, 2, 50, 3000, 60000])
+    cap = rng.choice([1, 2, 50, 3000, 60000, 400000])
     save = rng.choice([1, 3, 64, 1000, 1024])
     kw = {}
     if rng.random() < 0.5: kw['level_capacity'] = rng.choice([1024, 1500, 4096, 50000])
