@@ -325,7 +325,10 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "launches": nl[dom], "avg_launch_ms": ms[dom] / max(nl[dom], 1),
                          "algorithmic_bytes_per_launch": by[dom] / max(nl[dom], 1),
-                         "note": "integer/byte frontier work; the kernel is bound by instruction issue and dependent-instruction latency (issue slots ~60% active, DRAM ~1% of peak, DRAM bytes = algorithmic bytes), see profiles/README.md"},
+                         "note": "integer/byte frontier work: the kernels are bound by instruction issue and dependent-instruction latency, not by HBM "
+                                 "(ncu, final binary: check2_kernel 72% issue slots active, leaf_kernel 32-47% with 16-26% warps active because "
+                                 "only the unbounded items of a chunk are evaluated; DRAM 1-3% of peak, DRAM bytes = algorithmic bytes); "
+                                 "traffic is the DRAM byte count of ONE captured launch inside a good region, see profiles/README.md"},
             "kernel_ms_per_step": {K[i]: ms[i] / args.steps for i in range(5)},
             "kernel_launches_per_step": {K[i]: nl[i] / args.steps for i in range(5)},
             "device_ms_per_step": sum(s.kernel_ms_total for s in stats) / args.steps,

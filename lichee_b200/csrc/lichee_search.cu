@@ -548,6 +548,7 @@ struct Sched {                         // scheduler state, uploaded before and r
     long long trees_left;              // max_num_trees - valid trees found so far
     long long grow_calls, max_grow_calls;
     long long chunk_max, cap;
+    long long bfs_width;               // > 0: breadth-first prologue, whole levels until one is this wide
     long long checks, frontier_bytes, check_bytes, emit_bytes, chunks;
     int stop, stop_level;
 };
@@ -592,6 +593,7 @@ descend_kernel(DevNet net, Sched *sc) {
     const bool valid0 = lane < net.S;
     const bool valid1 = SPL == 2 && lane + 32 < net.S;
     const long long cap = sc->cap, chunk_max = sc->chunk_max, trees_left = sc->trees_left, max_grow = sc->max_grow_calls;
+    const long long bfs_width = sc->bfs_width;
     const long long limit = cap < (long long)kNarrowCap ? cap : (long long)kNarrowCap;
     // scheduler registers (meaningful in warp 0 only)
     long long grow = sc->grow_calls, checks = 0, fbytes = 0, cbytes = 0, ebytes = 0, chunks = 0;
@@ -608,7 +610,13 @@ descend_kernel(DevNet net, Sched *sc) {
         else if (lv >= L - 2) stop = kStopLeaf;        // the last two levels belong to check2 / emit2 / leaf
         else if (grow >= max_grow) stop = kStopGrow;
         else if (iter >= kNarrowIters) stop = kStopIters;
-        else {
+        else if (bfs_width > 0) {
+            // prologue of a sliced search: the whole level or nothing, until a level is wide enough to be cut
+            // (the host applies the same test before it launches, so the first chunk always goes through)
+            const long long pending = tail_s[lv] - head_s[lv];
+            if (pending >= bfs_width || pending > kNarrowMax || pending * (long long)ncand_s[lv] > limit) stop = kStopWide;
+            else B = pending;
+        } else {
             // expected complete trees below one item of this level: product of the fan-outs from here down
             double prod = 1.0;
             for (int l = lv + lane; l < L; l += 32) prod *= fmax(seen_s[l] ? fan_s[l] : (double)ncand_s[l], 1e-3);
@@ -2092,6 +2100,45 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     int es = 0;
     h->evn[0] = h->evn[1] = 0;
 
+    // A handful of items: the single-block scheduler walks the levels on its own until the last two levels are
+    // reached, a chunk gets wide, or the search ends -- one round trip for all of it.  bfs_width > 0: the
+    // breadth-first prologue of a sliced search (whole levels until one is that wide).
+    auto run_narrow = [&](long long bfs_width) -> int {
+        Sched *hs = h->h_sched;
+        for (int l = 0; l < L; l++) {
+            hs->head[l] = h->head[l]; hs->tail[l] = h->tail[l]; hs->ptr[l] = h->level(l);
+            hs->fan[l] = fan[l]; hs->seen[l] = seen[l] ? 1 : 0;
+        }
+        hs->trees_left = h->prm.max_num_trees - seq_base;
+        hs->grow_calls = st.num_grow_calls; hs->max_grow_calls = h->prm.max_num_grow_calls;
+        hs->chunk_max = h->chunk_max; hs->cap = h->cap; hs->bfs_width = bfs_width;
+        Sched *ds = static_cast<Sched *>(h->b_sched.p);
+        es ^= 1;
+        if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        h->ev_leaf[es] = false;
+        CK(cudaEventRecord(h->evk[es][0], h->stream));
+        CK(cudaMemcpyAsync(ds, hs, sizeof(Sched), cudaMemcpyHostToDevice, h->stream));
+        descend_kernel<SPL><<<1, kNarrowThreads, h->smem + (size_t)L * kMaxN, h->stream>>>(h->net, ds);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->evk[es][1], h->stream));
+        CK(cudaEventRecord(h->evk[es][2], h->stream));
+        h->evn[es] = 3;
+        CK(cudaMemcpyAsync(hs, ds, sizeof(Sched), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int l = 0; l < L; l++) {
+            h->head[l] = hs->head[l]; h->tail[l] = hs->tail[l]; fan[l] = hs->fan[l]; seen[l] = hs->seen[l] != 0;
+        }
+        st.num_checks += hs->checks;
+        st.num_grow_calls = hs->grow_calls;
+        st.frontier_bytes += hs->frontier_bytes;
+        st.kernel_bytes[LICHEE_K_CHECK] += hs->check_bytes;
+        st.kernel_bytes[LICHEE_K_EMIT] += hs->emit_bytes;
+        st.num_launches++;
+        st.kernel_launches[LICHEE_K_CHECK]++;
+        if (getenv("LICHEE_DEBUG")) fprintf(stderr, "narrow: %lld chunks, stop %d at level %d\n", hs->chunks, hs->stop, hs->stop_level);
+        return LICHEE_OK;
+    };
+
     bool list_full = false;                  // the ranked list held num_save trees at the last read-back
     // what emit2_kernel reported about the current fill of the last level: items that are not bounded, valid
     // trees below all of them (fill_items = 0: unknown, e.g. after the level was cut into slices)
@@ -2114,6 +2161,12 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 h->tail[lv] = b;
                 sliced = true;
                 if (a == b) break;
+            } else if (h->narrow && lv < L - 2 && width <= kNarrowMax &&
+                       width * (long long)h->cands[lv].size() <= std::min<long long>(h->cap, kNarrowCap)) {
+                // narrow levels of the prologue run on the device as well (every rank walks the same levels)
+                if (run_narrow(64ll * P) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
+                continue;
             }
         } else {
             for (int l = L - 1; l >= 0; l--) if (h->tail[l] > h->head[l]) { lv = l; break; }
@@ -2163,40 +2216,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         }
         if (leaf) fill_items = 0;                 // a chunk of the fill goes through the kernels: totals no longer apply
         if (sliced && lv < L - 2 && h->narrow && B <= kNarrowMax) {
-            // a handful of items: the single-block scheduler walks the levels on its own until the last
-            // level is reached, a chunk gets wide, or the search ends -- one round trip for all of it
-            Sched *hs = h->h_sched;
-            for (int l = 0; l < L; l++) {
-                hs->head[l] = h->head[l]; hs->tail[l] = h->tail[l]; hs->ptr[l] = h->level(l);
-                hs->fan[l] = fan[l]; hs->seen[l] = seen[l] ? 1 : 0;
-            }
-            hs->trees_left = h->prm.max_num_trees - seq_base;
-            hs->grow_calls = st.num_grow_calls; hs->max_grow_calls = h->prm.max_num_grow_calls;
-            hs->chunk_max = h->chunk_max; hs->cap = h->cap;
-            Sched *ds = static_cast<Sched *>(h->b_sched.p);
-            es ^= 1;
-            if (harvest_events(h, es) != LICHEE_OK) return LICHEE_ERR_CUDA;
-            h->ev_leaf[es] = false;
-            CK(cudaEventRecord(h->evk[es][0], h->stream));
-            CK(cudaMemcpyAsync(ds, hs, sizeof(Sched), cudaMemcpyHostToDevice, h->stream));
-            descend_kernel<SPL><<<1, kNarrowThreads, h->smem + (size_t)L * kMaxN, h->stream>>>(h->net, ds);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(h->evk[es][1], h->stream));
-            CK(cudaEventRecord(h->evk[es][2], h->stream));
-            h->evn[es] = 3;
-            CK(cudaMemcpyAsync(hs, ds, sizeof(Sched), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            for (int l = 0; l < L; l++) {
-                h->head[l] = hs->head[l]; h->tail[l] = hs->tail[l]; fan[l] = hs->fan[l]; seen[l] = hs->seen[l] != 0;
-            }
-            st.num_checks += hs->checks;
-            st.num_grow_calls = hs->grow_calls;
-            st.frontier_bytes += hs->frontier_bytes;
-            st.kernel_bytes[LICHEE_K_CHECK] += hs->check_bytes;
-            st.kernel_bytes[LICHEE_K_EMIT] += hs->emit_bytes;
-            st.num_launches++;
-            st.kernel_launches[LICHEE_K_CHECK]++;
-            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "narrow: %lld chunks, stop %d at level %d\n", hs->chunks, hs->stop, hs->stop_level);
+            if (run_narrow(0) != LICHEE_OK) return LICHEE_ERR_CUDA;
             if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
             continue;
         }
@@ -2280,8 +2300,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             list_full = h->h_meta->count >= (unsigned)h->prm.num_save || m >= (long long)h->prm.num_save;
             if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld bounded=%llu tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->n_bounded, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
-            // algorithmic bytes of the launch: the count word of every item, the item itself where it was evaluated
-            st.kernel_bytes[LICHEE_K_LEAF] += B * 4ll + (B - (long long)h->h_meta->n_bounded) * (long long)h->stride;
+            // algorithmic bytes of the launch: the count word of every item, the item itself where it was
+            // evaluated, the candidate records written
+            st.kernel_bytes[LICHEE_K_LEAF] += B * 4ll + (B - (long long)h->h_meta->n_bounded) * (long long)h->stride + m * (long long)sizeof(Cand);
             if (m > 0) {
                 if (launch_scan(h, lcnt, B, ~0ull >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
