@@ -44,11 +44,12 @@ extern "C" {
 #define LICHEE_STATUS_TREE_CAP   1u   /* stopped at max_num_trees   (Parameters.MAX_NUM_TREES)      */
 #define LICHEE_STATUS_GROW_CAP   2u   /* stopped at max_num_grow_calls (Parameters.MAX_NUM_GROW_CALLS) */
 
-#define LICHEE_K_CHECK   0        /* sum-rule check of every candidate extension             */
+#define LICHEE_K_CHECK   0        /* sum-rule check of every candidate extension (check_kernel,
+                                     check2_kernel, and the single-block scheduler descend_kernel) */
 #define LICHEE_K_SCAN    1        /* ordered exclusive scan of the pass counts                */
 #define LICHEE_K_EMIT    2        /* write surviving children to the next frontier level      */
 #define LICHEE_K_LEAF    3        /* error score of complete trees + threshold filter         */
-#define LICHEE_K_SELECT  4        /* block-level bitonic top-s selection                      */
+#define LICHEE_K_SELECT  4        /* sequence numbers, radix pre-selection, rank-merge top-s  */
 #define LICHEE_NUM_KERNELS 5
 
 typedef struct lichee_search lichee_search;   /* opaque handle: one constraint network on one GPU */
@@ -81,7 +82,8 @@ typedef struct lichee_search_stats {
     int64_t num_trees;           /* valid spanning trees found ("Found N valid tree(s)")        */
     int64_t num_grow_calls;      /* accepted partial trees + 1, the reference's numGrowCalls    */
     int64_t num_checks;          /* checkConstraint evaluations (candidate trees checked)       */
-    int64_t num_scored;          /* complete trees scored                                       */
+    int64_t num_scored;          /* complete valid trees ranked: scored, or excluded from the
+                                    ranked list by the lower bound of their partial tree        */
     int64_t num_launches;        /* kernels launched by lichee_search_run                       */
     int64_t frontier_bytes;      /* algorithmic HBM bytes moved through the frontier buffers    */
     double  kernel_ms_total;     /* CUDA-event time of the whole device search                  */

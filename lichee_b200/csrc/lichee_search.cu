@@ -18,10 +18,16 @@
 //   * The frontier is kept in HBM level by level and walked depth-first in chunks, so memory is
 //     bounded by (levels x level_capacity) and trees come out in a deterministic canonical order.
 //     check -> exclusive scan -> emit keeps that order without atomics.
-//   * The last level fuses check and scoring: complete trees are scored in double precision with a
-//     fixed-shape reduction, all trees of an item at once, and filtered against the current s-th
-//     best score without a square root; survivors go through an exact radix selection and a
-//     rank-merge into the device-resident ranked list.
+//   * Narrow chunks (the first descent, small networks) are scheduled on the device: one block walks
+//     the levels on its own (descend_kernel) instead of three launches and a host round trip per level.
+//   * The level above the last one (check2_kernel / emit2_kernel) decides the last node's pass masks
+//     for all its children with bit operations and totals each item's excess: a lower bound of the
+//     score of every tree below it.  Items whose bound already exceeds the s-th best kept score are
+//     counted and numbered, never read or scored again.
+//   * The last level (leaf_kernel) scores the remaining trees in double precision with a fixed-shape
+//     reduction, all trees of an item at once, filtered against the current s-th best score without
+//     a square root; survivors go through an exact radix selection and a rank-merge into the
+//     device-resident ranked list.
 //   No tensor cores: nothing here is a dense contraction.  No CPU fallback.
 #include <cuda_runtime.h>
 
@@ -779,9 +785,8 @@ descend_kernel(DevNet net, Sched *sc) {
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel 4: last level, sum-rule check and scoring fused.  A warp walks a contiguous run of
-// leaf-parent items (every node placed but the last); every passing choice p* for the last node is a
-// complete valid tree.
+// kernel 4: last level, scoring.  A warp walks runs of last-level items (every node placed but the last);
+// every passing choice p* for the last node is a complete valid tree.
 //   score = sqrt( sum over parents p, samples s of max(0, sum(children of p)[s] - VAF(p)[s])^2 )
 // (PHYTree.computeErrorScore, PHYTree.java:214-233).  The reference adds the positive terms one
 // after another; with noisy centroids a tree has thousands of them, i.e. thousands of dependent
@@ -1132,10 +1137,10 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
     }
 }
 
-// At the last level the sum-rule check and the scoring share all their sums, so one kernel does
-// both: it writes the pass mask + count of every item (for the scan that numbers the valid trees)
-// and appends the trees that beat the threshold with a provisional sequence number; seq_fixup_kernel
-// turns that into the canonical one once the scan has run.
+// Last level: the pass mask + count of every item were written by emit2_kernel (for the scan that numbers
+// the valid trees); this kernel scores the trees of the items that are not bounded and appends those that
+// beat the threshold with a provisional sequence number; seq_fixup_kernel turns that into the canonical
+// one once the scan has run.
 template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__restrict__ fit, long long item_base,
