@@ -332,6 +332,9 @@ def main():
             "kernel_ms_per_step": {K[i]: ms[i] / args.steps for i in range(5)},
             "kernel_launches_per_step": {K[i]: nl[i] / args.steps for i in range(5)},
             "device_ms_per_step": sum(s.kernel_ms_total for s in stats) / args.steps,
+            "timing": "value/ms_per_step: host clock between (barrier + cuda synchronize) pairs around the K steps, max over ranks "
+                      "(it contains everything, host round trips and the merge included); device_ms_per_step and kernel_ms_per_step: "
+                      "CUDA events on the library's own stream (rank 0)",
         }
         if world == 1:
             line["bundled_datasets_build_search_ms"] = bundled_search_times(lichee_b200, not args.no_cpu_baseline)
