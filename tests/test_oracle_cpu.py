@@ -144,3 +144,34 @@ def test_reference_enumeration_order_depends_on_search_history():
         if (a["all_parents"][:k] != b["all_parents"][:k]).any():
             diverged += 1
     assert diverged >= 3
+
+
+def test_partial_tree_score_is_a_lower_bound():
+    """What the device's pruning rests on: with non-negative VAFs the canonical score
+    of a tree WITHOUT its last one or two nodes (same fixed-shape reduction, the missing rows contribute
+    exact zeros) never exceeds the score of the complete tree -- in floating point, not only in real
+    arithmetic.  Checked on the ranked trees of random synthetic networks."""
+    from lichee_b200.synth import make_instance
+    checked = 0
+    for seed in range(8):
+        net, prm = make_instance(9 + seed, 3 + 4 * (seed % 3), seed=100 + seed, noise=0.02)
+        vaf = np.array(net.aaf, dtype=np.float64)
+        assert (vaf >= 0).all()
+        ref = oracle.canonical_search(net.adj, vaf, prm.vaf_error_margin, top_s=300, max_trees=200000)
+        sigma = [int(x) for x in ref["sigma"]]
+        for k in range(len(ref["scores"])):
+            parent = [int(x) for x in ref["parents"][k]]
+            ok, full = oracle.canonical_eval_tree(vaf, prm.vaf_error_margin, parent)
+            assert ok and full == ref["scores"][k]
+            for drop in (1, 2):
+                gone = set(sigma[-drop:])
+                keep = [v for v in range(len(parent)) if v not in gone]
+                if any(parent[v] in gone for v in keep):
+                    continue                      # a kept node hangs under a dropped one: not a partial tree
+                new_id = {v: i for i, v in enumerate(keep)}
+                sub_parent = [-1 if parent[v] < 0 else new_id[parent[v]] for v in keep]
+                ok2, part = oracle.canonical_eval_tree(vaf[keep], prm.vaf_error_margin, sub_parent)
+                assert ok2, "a sub-tree of a valid tree is valid"
+                assert part <= full, (seed, k, drop, part, full)
+                checked += 1
+    assert checked > 500
