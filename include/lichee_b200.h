@@ -39,10 +39,20 @@ extern "C" {
 #define LICHEE_MAX_NODES    128       /* network nodes including the germline root (node 0)      */
 #define LICHEE_MAX_SAMPLES   64
 #define LICHEE_MAX_SAVE    1024       /* upper bound on -s                                       */
+#define LICHEE_DEFAULT_REF_ORDER_BUDGET (1ll << 22)   /* grow() calls; every bundled ccRCC / HGSC network needs < 2^18 */
 
 /* status bits returned in lichee_search_stats.status */
 #define LICHEE_STATUS_TREE_CAP   1u   /* stopped at max_num_trees   (Parameters.MAX_NUM_TREES)      */
 #define LICHEE_STATUS_GROW_CAP   2u   /* stopped at max_num_grow_calls (Parameters.MAX_NUM_GROW_CALLS) */
+#define LICHEE_STATUS_CANONICAL_ORDER 4u /* the ranked list follows the CANONICAL enumeration order, not the
+                                         reference's discovery order: ties in score, the trees kept under a
+                                         binding MAX_NUM_TREES and the order of a node's children (hence the
+                                         last bits of a score) may differ from the Java implementation.  Set when
+                                         the reference-order replay is switched off (ref_order_budget < 0), when
+                                         the search is sharded (part_count > 1, lichee_search_run_slice) or when
+                                         the replay did not finish within ref_order_budget grow() calls.  Clear:
+                                         counts, ranked trees, treeNodes order and scores are those of
+                                         PHYNetwork.getLineageTrees + evaluateLineageTrees, bit for bit.        */
 
 #define LICHEE_K_CHECK   0        /* sum-rule check of every candidate extension (check_kernel,
                                      check2_kernel, and the single-block scheduler descend_kernel) */
@@ -75,7 +85,10 @@ typedef struct lichee_search_params {
     int32_t part_rank;
     int32_t part_count;
     int64_t level_capacity;      /* frontier items per tree level kept in HBM; 0 = default      */
-    int64_t reserved[4];
+    int64_t ref_order_budget;    /* grow() calls the reference-order replay may spend before the search
+                                    falls back to the canonical order (LICHEE_STATUS_CANONICAL_ORDER):
+                                    0 = default (LICHEE_DEFAULT_REF_ORDER_BUDGET), < 0 = canonical order only */
+    int64_t reserved[3];
 } lichee_search_params;
 
 typedef struct lichee_search_stats {

@@ -19,6 +19,8 @@ MAX_SAMPLES = 64
 MAX_SAVE = 1024
 STATUS_TREE_CAP = 1
 STATUS_GROW_CAP = 2
+STATUS_CANONICAL_ORDER = 4       # ties / cap prefix / child order follow the canonical order, not the reference's
+DEFAULT_REF_ORDER_BUDGET = 1 << 22
 
 EXPORTED_SYMBOLS = [
     "lichee_default_params", "lichee_search_create", "lichee_search_run", "lichee_search_run_slice",
@@ -40,7 +42,7 @@ class SearchParams(ctypes.Structure):
                 ("device", ctypes.c_int32), ("max_num_trees", ctypes.c_int64),
                 ("max_num_grow_calls", ctypes.c_int64), ("part_rank", ctypes.c_int32),
                 ("part_count", ctypes.c_int32), ("level_capacity", ctypes.c_int64),
-                ("reserved", ctypes.c_int64 * 4)]
+                ("ref_order_budget", ctypes.c_int64), ("reserved", ctypes.c_int64 * 3)]
 
 
 class SearchStats(ctypes.Structure):
@@ -183,8 +185,12 @@ class LineageSearch:
 
     def __init__(self, adj, vaf, vaf_error_margin=Parameters.VAF_ERROR_MARGIN, num_save=1,
                  max_num_trees=Parameters.MAX_NUM_TREES, max_num_grow_calls=Parameters.MAX_NUM_GROW_CALLS,
-                 device=0, part_rank=0, part_count=1, level_capacity=0):
+                 device=0, part_rank=0, part_count=1, level_capacity=0, ref_order_budget=0):
+        """ref_order_budget: grow() calls the reference-order replay may spend (0 = default 2^22, < 0 = canonical
+        order only); see LICHEE_STATUS_CANONICAL_ORDER in include/lichee_b200.h."""
         vaf = np.ascontiguousarray(vaf, dtype=np.float64)
+        if vaf.ndim != 2 or len(adj) != vaf.shape[0]:
+            raise LicheeError(-1, f"adjacency lists ({len(adj)}) and centroid matrix {vaf.shape} disagree on the node count")
         self.n, self.S = vaf.shape
         off, idx = _csr(adj)
         p = default_params()
@@ -195,6 +201,7 @@ class LineageSearch:
         p.max_num_grow_calls = max_num_grow_calls
         p.part_rank, p.part_count = part_rank, part_count
         p.level_capacity = level_capacity
+        p.ref_order_budget = ref_order_budget
         self.params = p
         self._h = ctypes.c_void_p()
         _ck(lib().lichee_search_create(ctypes.byref(self._h), self.n, self.S, off.ctypes.data, idx.ctypes.data,

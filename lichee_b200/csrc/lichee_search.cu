@@ -44,6 +44,7 @@
 #include <vector>
 
 #include "../../include/lichee_b200.h"
+#include "lichee_replay.cuh"
 
 namespace {
 
@@ -89,6 +90,7 @@ struct DevNet {
     int prune;               // every VAF >= 0: a partial tree's excess is a lower bound of every completion's
     double margin;
     uint4 static_both;       // level L-2, bit i: childless candidate i of node v also takes the last node u
+    const uint8_t *desc_rows; // [n]     rows in DESCENDING node id: the parent order of computeErrorScore (PHYNode.compareTo)
 };
 
 // Frontier item layout: an item is W = stride/4 words; the parent (row index q) of tree position t
@@ -1601,18 +1603,18 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
     const int wl = item_byte(last_level, wstride) >> 2, sh = 8 * (item_byte(last_level, wstride) & 3);
     for (unsigned t = wid; t < newc; t += kSelThreads / 32) {
         const Cand c = res[t];
-        unsigned w = 0xffffffffu;
-        if (lane < wstride) {
+        for (int j = lane; j < wstride; j += 32) {      // (reference-order records are 2 x stride bytes: up to 64 words)
+            unsigned w;
             if (c.origin & 0x80000000u) {
-                w = tree_cur[(size_t)(c.origin & 0x7fffffffu) * wstride + lane];
+                w = tree_cur[(size_t)(c.origin & 0x7fffffffu) * wstride + j];
             } else if (external_records) {
                 const unsigned *src = reinterpret_cast<const unsigned *>(records + (size_t)c.origin * record_bytes + 24);
-                w = src[lane];
+                w = src[j];
             } else {
-                w = leaf_items[(size_t)c.origin * wstride + lane];
-                if (lane == wl) w = (w & ~(0xffu << sh)) | (c.pstar << sh);
+                w = leaf_items[(size_t)c.origin * wstride + j];
+                if (j == wl) w = (w & ~(0xffu << sh)) | (c.pstar << sh);
             }
-            tree_next[(size_t)t * wstride + lane] = w;
+            tree_next[(size_t)t * wstride + j] = w;
         }
     }
     for (int t = threadIdx.x; t < (int)newc; t += kSelThreads) top_next[t] = res[t];
@@ -1776,6 +1778,198 @@ __global__ void export_records(const TopMeta *meta, const Cand *top, const unsig
         reinterpret_cast<unsigned *>(r + 24)[threadIdx.x] = valid ? tree[(size_t)t * wstride + threadIdx.x] : 0xffffffffu;
 }
 
+// ------------------------------------------------------------------------------------------
+// Reference-order mode (lichee_replay.cuh): the reference's own traversal, replayed by one warp.
+//
+// replay_kernel   one block; the state blob lives in shared memory when it fits next to the centroid
+//                 matrix (every real data set), else it is used in place in global memory.  Lane 0 runs
+//                 the transitions; at R_CHECK the warp evaluates the sum rule (lanes own samples, the
+//                 running child sums psum[] are lane-private), at R_RECORD it writes the tree as one
+//                 record: {score, seq, part, valid, A[stride], B[stride]} with A = the nodes in the order
+//                 they joined the tree (treeNodes without the root) and B = their parents, both as ROW
+//                 indices in the frontier-item byte layout (item_byte).  Resumable: returns when the
+//                 record buffer is full, the step quota is used up or the grow() budget is reached.
+// score_ref_kernel one warp per recorded tree: PHYTree.computeErrorScore (PHYTree.java:214-233) in the
+//                 reference's accumulation order -- parents in descending node id, per parent the
+//                 samples 0..S-1, children added in insertion order, err += (sum - VAF)^2 one term after
+//                 the other, then Math.sqrt.  No FMA contraction (explicit _rn intrinsics).
+// ------------------------------------------------------------------------------------------
+struct ReplayOut {
+    long long num_grow, num_checks, num_trees, steps;
+    int status, rec_count;
+};
+
+constexpr int kReplayThreads = 128;
+constexpr int kReplaySmemMax = 225 * 1024;  // dynamic shared memory the replay may take (227 KB per block on sm_100a)
+constexpr int kReplayRecCap = 1 << 15;       // trees one replay launch may record before the batch is scored and merged
+
+template <int SPL>
+__global__ void __launch_bounds__(kReplayThreads, 1)
+replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const double *__restrict__ vaf_g, int S,
+              double margin, unsigned char *records, long long record_bytes, int rec_cap, int L, int stride,
+              long long step_quota, long long grow_limit, ReplayOut *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vaf_s = reinterpret_cast<double *>(smem_raw);
+    const int SP = lay.SP;
+    const unsigned vaf_bytes = (unsigned)lay.n * SP * 8u;
+    unsigned char *blob = blob_in_smem ? smem_raw + vaf_bytes : blob_g;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(vaf_g);
+        uint4 *dst = reinterpret_cast<uint4 *>(vaf_s);
+        for (unsigned i = threadIdx.x; i < vaf_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        if (blob_in_smem) {
+            const uint4 *bs = reinterpret_cast<const uint4 *>(blob_g);
+            uint4 *bd = reinterpret_cast<uint4 *>(blob);
+            for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        replay::State s = replay::bind(blob, lay);
+        replay::Header *h = s.h;
+        const bool valid0 = lane < S, valid1 = SPL == 2 && lane + 32 < S;
+        const int W = stride >> 2;
+        int rec_count = 0;
+        long long steps = 0;
+        for (;;) {
+            int r = replay::R_STOP;
+            if (lane == 0) {
+                // transitions up to the next piece of warp work
+                while (steps < step_quota && h->num_grow < grow_limit) {
+                    steps++;
+                    r = replay::step(s, rec_count < rec_cap);
+                    if (r != replay::R_CONTINUE) break;
+                }
+                if (r == replay::R_CONTINUE) r = replay::R_STOP;     // quota or budget used up between two transitions
+            }
+            __syncwarp();
+            r = __shfl_sync(kFull, r, 0);
+            if (r == replay::R_STOP) break;
+            if (r == replay::R_CHECK) {
+                // t.checkConstraint(u) with v appended (PHYTree.java:156-174): running sum of u's children
+                const int u = h->cu, v = h->cv, k = h->ck, prev = h->cprev;
+                double x0, x1, a0, a1, p0 = 0.0, p1 = 0.0;
+                load_row<SPL>(vaf_s, v, SP, lane, x0, x1);
+                load_row<SPL>(vaf_s, u, SP, lane, a0, a1);
+                if (prev != replay::kNoChild) load_row<SPL>(s.psum, prev, SP, lane, p0, p1);
+                const double s0 = __dadd_rn(p0, x0), s1 = __dadd_rn(p1, x1);
+                if (SPL == 2) reinterpret_cast<double2 *>(s.psum)[k * 32 + lane] = make_double2(s0, s1);
+                else s.psum[k * SP + lane] = s0;
+                bool bad = valid0 && s0 > __dadd_rn(a0, margin);
+                if (SPL == 2) bad |= valid1 && s1 > __dadd_rn(a1, margin);
+                const bool ok = !__any_sync(kFull, bad);
+                if (lane == 0) h->ok = ok ? 1 : 0;
+            } else {                                     // R_RECORD
+                unsigned char *rp = records + (size_t)rec_count * record_bytes;
+                if (lane == 0) {
+                    *reinterpret_cast<double *>(rp) = 0.0;
+                    *reinterpret_cast<long long *>(rp + 8) = h->num_trees;
+                    *reinterpret_cast<int *>(rp + 16) = 0;
+                    *reinterpret_cast<int *>(rp + 20) = 1;
+                }
+                if (lane < W) {
+                    unsigned a = 0, b = 0;
+                    for (int q = 3; q >= 0; q--) {
+                        const int i = q * W + lane;      // tree position i <-> treeNodes[i + 1]
+                        unsigned ab = 0xffu, bb = 0xffu;
+                        if (i < L) { ab = s.tn[i + 1]; bb = s.par[ab]; }
+                        a = (a << 8) | ab;
+                        b = (b << 8) | bb;
+                    }
+                    reinterpret_cast<unsigned *>(rp + 24)[lane] = a;
+                    reinterpret_cast<unsigned *>(rp + 24 + stride)[lane] = b;
+                }
+                rec_count++;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            out->num_grow = h->num_grow; out->num_checks = h->num_checks; out->num_trees = h->num_trees;
+            out->steps = steps; out->status = h->status; out->rec_count = rec_count;
+        }
+    }
+    __syncthreads();
+    if (blob_in_smem) {
+        uint4 *bd = reinterpret_cast<uint4 *>(blob_g);
+        const uint4 *bs = reinterpret_cast<const uint4 *>(blob);
+        for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
+    }
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(kThreads, 2)
+score_ref_kernel(DevNet net, unsigned char *records, long long record_bytes, int count, Cand *__restrict__ cands,
+                 TopMeta *meta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vaf_s = reinterpret_cast<double *>(smem_raw);
+    uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    __shared__ uint8_t desc_s[kMaxN];
+    stage_network(net, 0, vaf_s, cand_s);
+    for (int i = threadIdx.x; i < net.n; i += blockDim.x) desc_s[i] = net.desc_rows[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta->n_cand = (unsigned long long)count;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int SP = net.SP, W = net.stride >> 2, L = net.L;
+    const int rmax = (L - 1) / W;
+    const bool valid0 = lane < net.S, valid1 = SPL == 2 && lane + 32 < net.S;
+    const int warp0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), nwarps = gridDim.x * kWarpsPerBlock;
+    for (int t = warp0; t < count; t += nwarps) {
+        unsigned char *rp = records + (size_t)t * record_bytes;
+        const unsigned wA = lane < W ? reinterpret_cast<const unsigned *>(rp + 24)[lane] : 0xffffffffu;
+        const unsigned wB = lane < W ? reinterpret_cast<const unsigned *>(rp + 24 + net.stride)[lane] : 0xffffffffu;
+        unsigned pm[4];
+        parent_presence(wB, rmax, pm);
+        double err = 0.0;
+        for (int kk = 0; kk < net.n; kk++) {
+            const unsigned p = desc_s[kk];
+            if (!((pm[p >> 5] >> (p & 31)) & 1u)) continue;
+            const unsigned m = __vcmpeq4(wB, p * 0x01010101u);
+            double s0 = 0.0, s1 = 0.0;
+            for (int r = 0; r <= rmax; r++) {
+                unsigned kids = __ballot_sync(kFull, (m >> (8 * r)) & 1u);
+                while (kids) {                           // children in insertion (treeNodes) order
+                    const int j = __ffs(kids) - 1;
+                    kids &= kids - 1;
+                    const unsigned c = (__shfl_sync(kFull, wA, j) >> (8 * r)) & 0xffu;
+                    double x0, x1;
+                    load_row<SPL>(vaf_s, (int)c, SP, lane, x0, x1);
+                    s0 = __dadd_rn(s0, x0);
+                    if (SPL == 2) s1 = __dadd_rn(s1, x1);
+                }
+            }
+            double a0, a1;
+            load_row<SPL>(vaf_s, (int)p, SP, lane, a0, a1);
+            double t0 = 0.0, t1 = 0.0;
+            if (valid0 && s0 > a0) { const double dd = __dsub_rn(s0, a0); t0 = __dmul_rn(dd, dd); }
+            if (SPL == 2 && valid1 && s1 > a1) { const double dd = __dsub_rn(s1, a1); t1 = __dmul_rn(dd, dd); }
+            unsigned pos = __ballot_sync(kFull, t0 > 0.0);
+            while (pos) {                                // samples 0..31, one after the other
+                const int j = __ffs(pos) - 1;
+                pos &= pos - 1;
+                err = __dadd_rn(err, __shfl_sync(kFull, t0, j));
+            }
+            if (SPL == 2) {
+                pos = __ballot_sync(kFull, t1 > 0.0);
+                while (pos) {                            // samples 32..63
+                    const int j = __ffs(pos) - 1;
+                    pos &= pos - 1;
+                    err = __dadd_rn(err, __shfl_sync(kFull, t1, j));
+                }
+            }
+        }
+        if (lane == 0) {
+            const double score = __dsqrt_rn(err);
+            *reinterpret_cast<double *>(rp) = score;
+            Cand c;
+            c.score = score;
+            c.seq = *reinterpret_cast<const long long *>(rp + 8);
+            c.part = 0; c.origin = (unsigned)t; c.pstar = 0; c.pad = 0;
+            cands[t] = c;
+        }
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1831,6 +2025,7 @@ struct CtxPool {
     std::mutex mu;
     std::multimap<int, DevCtx> free_list;
     bool attrs_set[64] = {};
+    bool attrs2_set[64] = {};
     bool get(int dev, DevCtx &c) {
         std::lock_guard<std::mutex> g(mu);
         auto it = free_list.find(dev);
@@ -1887,6 +2082,14 @@ struct lichee_search {
     std::vector<uint8_t> h_tree;
     DevNet net{};
     size_t smem = 0, smem_leaf = 0;
+    // reference-order mode (lichee_replay.cuh)
+    bool cyclic = false;                     // the network has a directed cycle: only the replay can search it
+    bool ref_result = false;                 // the ranked list on the host came from the replay (records of 2 x stride bytes)
+    replay::Layout rlay{};
+    std::vector<unsigned char> rblob0;       // initial state of getLineageTrees(), uploaded before every replay
+    bool rblob_in_smem = false;
+    DevBuf b_rblob, b_rrec, b_rout;          // state blob, record buffer, ReplayOut
+    ReplayOut *h_rout = nullptr;             // pinned
 
     unsigned *level(int lv) { return static_cast<unsigned *>(b_level[lv].p); }
     uint4 *d_mask() { return static_cast<uint4 *>(b_mask.p); }
@@ -1955,12 +2158,13 @@ int launch_scan(lichee_search *h, const unsigned *cnt, long long n_items, unsign
 
 // Final selection: merge `m_hint` candidates (already bounded by the caller) into the ranked list.
 int run_select(lichee_search *h, const Cand *cands, long long cand_cap, const unsigned *leaf_items, int external,
-               const unsigned char *records, long long record_bytes) {
+               const unsigned char *records, long long record_bytes, int words = 0) {
     const size_t sm = sizeof(Cand) * 3 * kSelTile;
+    if (words == 0) words = h->stride >> 2;
     select_kernel<<<1, kSelThreads, sm, h->stream>>>(h->d_meta(), h->prm.num_save, cands, cand_cap,
                                                      h->d_top(h->flip), h->d_top(h->flip ^ 1),
                                                      h->d_tree(h->flip), h->d_tree(h->flip ^ 1), leaf_items,
-                                                     h->stride >> 2, h->L - 1, external, records, record_bytes);
+                                                     words, h->L - 1, external, records, record_bytes);
     CK(cudaGetLastError());
     h->flip ^= 1;
     h->stats.num_launches++;
@@ -2017,10 +2221,11 @@ int fetch_top(lichee_search *h) {
     CK(cudaStreamSynchronize(h->stream));
     const unsigned count = h->h_meta->count;
     h->h_top.resize(count);
-    h->h_tree.assign((size_t)count * h->stride, 0xff);
+    const size_t tb = h->ref_result ? 2 * (size_t)h->stride : (size_t)h->stride;
+    h->h_tree.assign((size_t)count * tb, 0xff);
     if (count) {
         CK(cudaMemcpyAsync(h->h_top.data(), h->d_top(h->flip), sizeof(Cand) * count, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_tree.data(), h->d_tree(h->flip), (size_t)count * h->stride, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_tree.data(), h->d_tree(h->flip), (size_t)count * tb, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
     h->stats.num_saved = count;
@@ -2395,6 +2600,132 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     return finish();
 }
 
+// Reference-order search: replay PHYNetwork.grow on the device, score the discovered trees in the
+// reference's accumulation order, rank by (score, discovery index) -- Collections.sort is stable.
+// `completed` is false when the replay ran out of its budget of grow() calls before the reference's own
+// search would have ended; the caller then falls back to the canonical search.
+template <int SPL>
+int run_reference_order(lichee_search *h, bool &completed) {
+    completed = false;
+    lichee_search_stats &st = h->stats;
+    st = lichee_search_stats{};
+    const long long budget = h->prm.ref_order_budget > 0 ? h->prm.ref_order_budget : LICHEE_DEFAULT_REF_ORDER_BUDGET;
+    const replay::Header *h0 = reinterpret_cast<const replay::Header *>(h->rblob0.data());
+    const long long rb = 24 + 2ll * h->stride;
+    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
+    h->flip = 0;
+    h->ref_result = true;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int status = h0->status;
+    long long num_grow = 0, num_checks = 0, num_trees = 0;
+    if (status == replay::S_RUNNING) {
+        CK(cudaMemcpyAsync(h->b_rblob.p, h->rblob0.data(), h->rlay.total, cudaMemcpyHostToDevice, h->stream));
+        ReplayOut *d_out = static_cast<ReplayOut *>(h->b_rout.p);
+        const size_t smem = (size_t)h->n * h->SP * sizeof(double) + (h->rblob_in_smem ? h->rlay.total : 0);
+        // record buffer: small for the first launch (most real searches end inside it), full size afterwards
+        int rec_cap = 4096;
+        for (;;) {
+            if (ensure(h, h->b_rrec, (size_t)rb * rec_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            unsigned char *rec = static_cast<unsigned char *>(h->b_rrec.p);
+            CK(cudaEventRecord(h->evk[0][0], h->stream));
+            replay_kernel<SPL><<<1, kReplayThreads, smem, h->stream>>>(
+                h->rlay, static_cast<unsigned char *>(h->b_rblob.p), h->rblob_in_smem ? 1 : 0, h->net.vaf, h->S,
+                h->prm.vaf_error_margin, rec, rb, rec_cap, h->L, h->stride, 1ll << 22, budget, d_out);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->evk[0][1], h->stream));
+            CK(cudaMemcpyAsync(h->h_rout, d_out, sizeof(ReplayOut), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            st.num_launches++;
+            st.kernel_launches[LICHEE_K_CHECK]++;
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h->evk[0][0], h->evk[0][1]));
+            st.kernel_ms[LICHEE_K_CHECK] += ms;
+            status = h->h_rout->status;
+            num_grow = h->h_rout->num_grow; num_checks = h->h_rout->num_checks; num_trees = h->h_rout->num_trees;
+            const int m = h->h_rout->rec_count;
+            st.kernel_bytes[LICHEE_K_CHECK] += (long long)m * rb;
+            if (m > 0) {
+                // score the batch (one warp per tree) and merge it into the ranked list
+                if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)std::max(m, kSelTile)) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                const int grid = (int)std::min<long long>(148 * 2, (m + kWarpsPerBlock - 1) / kWarpsPerBlock);
+                CK(cudaEventRecord(h->evk[0][2], h->stream));
+                score_ref_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(h->net, rec, rb, m, h->d_cands(0), h->d_meta());
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(h->evk[0][3], h->stream));
+                st.num_launches++;
+                st.kernel_launches[LICHEE_K_LEAF]++;
+                st.kernel_bytes[LICHEE_K_LEAF] += (long long)m * (rb + (long long)sizeof(Cand));
+                long long mm = m;
+                int src = 0;
+                bool radix = false;
+                if (mm > kSelTile && run_radix_select(h, mm, radix) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (radix) src = 1;
+                else if (run_tournament(h, mm, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (run_select(h, h->d_cands(src), mm, nullptr, 1, rec, rb, h->stride >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                CK(cudaEventRecord(h->evk[0][4], h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                CK(cudaEventElapsedTime(&ms, h->evk[0][2], h->evk[0][3])); st.kernel_ms[LICHEE_K_LEAF] += ms;
+                CK(cudaEventElapsedTime(&ms, h->evk[0][3], h->evk[0][4])); st.kernel_ms[LICHEE_K_SELECT] += ms;
+                st.kernel_bytes[LICHEE_K_SELECT] += (long long)m * (long long)sizeof(Cand);
+            }
+            if (status != replay::S_RUNNING) break;
+            if (num_grow >= budget) break;
+            rec_cap = kReplayRecCap;
+        }
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    st.kernel_ms_total = ms;
+    st.num_trees = num_trees;
+    st.num_grow_calls = num_grow;
+    st.num_checks = num_checks;
+    st.num_scored = num_trees;
+    if (status == replay::S_RUNNING) return LICHEE_OK;          // budget used up: not the reference's answer yet
+    completed = true;
+    if (status == replay::S_TREE_CAP) st.status |= LICHEE_STATUS_TREE_CAP;
+    if (status == replay::S_GROW_CAP) st.status |= LICHEE_STATUS_GROW_CAP;
+    return fetch_top(h);
+}
+
+// getLineageTrees + evaluateLineageTrees.  Reference order first (exact, sequential, budgeted); the
+// canonical parallel search when the replay is off, the search is sharded, or the budget ran out.
+int run_whole(lichee_search *h) {
+    const bool want_ref = h->prm.ref_order_budget >= 0 && h->prm.part_count <= 1;
+    lichee_search_stats ref_stats{};
+    bool tried = false;
+    if (want_ref) {
+        bool completed = false;
+        const int rc = h->SP == 32 ? run_reference_order<1>(h, completed) : run_reference_order<2>(h, completed);
+        if (rc != LICHEE_OK) return rc;
+        if (completed) return LICHEE_OK;
+        ref_stats = h->stats;
+        tried = true;
+    }
+    h->ref_result = false;
+    if (h->cyclic) {
+        set_err(tried ? "constraint network has a directed cycle and the reference-order replay did not finish within "
+                        "ref_order_budget grow() calls; the canonical parallel search needs a DAG"
+                      : "constraint network has a directed cycle: only the reference-order replay (ref_order_budget >= 0, "
+                        "part_count <= 1) can search it");
+        return LICHEE_ERR_CYCLIC;
+    }
+    const int rc = h->SP == 32 ? run_search<1>(h, h->prm.part_rank, h->prm.part_count, false)
+                               : run_search<2>(h, h->prm.part_rank, h->prm.part_count, false);
+    if (rc != LICHEE_OK) return rc;
+    h->stats.status |= LICHEE_STATUS_CANONICAL_ORDER;
+    if (tried) {                                            // the time the abandoned replay took is part of the search
+        h->stats.kernel_ms_total += ref_stats.kernel_ms_total;
+        h->stats.kernel_ms[LICHEE_K_CHECK] += ref_stats.kernel_ms[LICHEE_K_CHECK];
+        h->stats.kernel_ms[LICHEE_K_LEAF] += ref_stats.kernel_ms[LICHEE_K_LEAF];
+        h->stats.kernel_ms[LICHEE_K_SELECT] += ref_stats.kernel_ms[LICHEE_K_SELECT];
+        h->stats.num_launches += ref_stats.num_launches;
+        for (int i = 0; i < LICHEE_NUM_KERNELS; i++) h->stats.kernel_launches[i] += ref_stats.kernel_launches[i];
+    }
+    return LICHEE_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -2450,6 +2781,7 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_sched);
     give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag);
     give_back(h, h->b_lmask); give_back(h, h->b_lcnt);
+    give_back(h, h->b_rblob); give_back(h, h->b_rrec); give_back(h, h->b_rout);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     if (h->stream) {
         DevCtx c;
@@ -2477,36 +2809,39 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         set_err("lichee_search_create: parameter out of range (num_save 1..%d)", LICHEE_MAX_SAVE);
         return LICHEE_ERR_INVALID;
     }
-    // parents of every node, ascending id, duplicates removed; DAG test (Kahn)
-    std::vector<std::vector<int>> par(n);
+    // parents of every node, ascending id.  Dropped: duplicates (PHYNetwork.addEdge refuses them), self loops
+    // and edges into the root (the root is in the tree from the start, so neither the reference nor this
+    // library ever follows one).  radj: the adjacency lists that remain, in list order.
+    if (adj_off[0] != 0) { set_err("adj_off[0] must be 0"); return LICHEE_ERR_INVALID; }
+    if (!(params->vaf_error_margin == params->vaf_error_margin) || std::isinf(params->vaf_error_margin)) {
+        set_err("vaf_error_margin is not finite"); return LICHEE_ERR_INVALID;
+    }
+    for (size_t i = 0; i < (size_t)n * S; i++)
+        if (!std::isfinite(vaf[i])) { set_err("vaf[%zu] is not finite", i); return LICHEE_ERR_INVALID; }
+    std::vector<std::vector<int>> par(n), radj(n);
     std::vector<int> indeg(n, 0);
     for (int u = 0; u < n; u++) {
         if (adj_off[u + 1] < adj_off[u]) { set_err("adj_off not monotone"); return LICHEE_ERR_INVALID; }
         for (int k = adj_off[u]; k < adj_off[u + 1]; k++) {
             const int v = adj_idx[k];
             if (v < 0 || v >= n) { set_err("edge target %d out of range", v); return LICHEE_ERR_INVALID; }
-            if (std::find(par[v].begin(), par[v].end(), u) == par[v].end()) par[v].push_back(u);
+            if (v == u || v == 0) continue;
+            if (std::find(radj[u].begin(), radj[u].end(), v) == radj[u].end()) { radj[u].push_back(v); par[v].push_back(u); }
         }
     }
     for (int v = 0; v < n; v++) { std::sort(par[v].begin(), par[v].end()); indeg[v] = (int)par[v].size(); }
+    bool cyclic = false;
     {
-        std::vector<int> deg = indeg, q;
+        std::vector<int> deg = indeg, q;               // Kahn
         for (int v = 0; v < n; v++) if (deg[v] == 0) q.push_back(v);
         size_t qi = 0;
         while (qi < q.size()) {
             const int u = q[qi++];
-            for (int k = adj_off[u]; k < adj_off[u + 1]; k++) {
-                const int v = adj_idx[k];
-                // count each distinct edge once
-                bool first = true;
-                for (int k2 = adj_off[u]; k2 < k; k2++) if (adj_idx[k2] == v) first = false;
-                if (first && --deg[v] == 0) q.push_back(v);
-            }
+            for (int v : radj[u]) if (--deg[v] == 0) q.push_back(v);
         }
-        if ((int)q.size() != n) {
-            set_err("constraint network has a directed cycle; the parent-choice search needs a DAG");
-            return LICHEE_ERR_CYCLIC;
-        }
+        // A directed cycle: the parent-choice search needs a DAG, the reference's Gabow-Myers search does not
+        // (PHYNetwork.java:114-118,185-232 can produce one inside a group); only the replay can run it.
+        cyclic = (int)q.size() != n;
     }
     if (lichee_device_count() < 1) {
         set_err("no CUDA device available: lichee_b200 has no CPU fallback");
@@ -2520,8 +2855,8 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->SP = S <= 32 ? 32 : 64;
     h->stride = std::max(16, ((h->L + 15) / 16) * 16);
     // a tree exists only if the root has children (PHYNetwork.java:557) and every other node a parent
-    h->no_trees = adj_off[1] == adj_off[0] && n > 1;
-    if (indeg[0] != 0) h->no_trees = true;   // the root must be a source
+    h->no_trees = radj[0].empty() && n > 1;
+    h->cyclic = cyclic;
     for (int v = 1; v < n; v++) if (par[v].empty()) h->no_trees = true;
     if (n == 1) h->no_trees = true;          // getLineageTrees returns an empty list
     // sigma: non-root nodes by descending VAF mass, ties by ascending id
@@ -2552,7 +2887,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
             CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
             for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
-            CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta) + sizeof(Sched)));
+            CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta) + sizeof(Sched) + sizeof(ReplayOut)));
         }
     }
     const int Lp = std::max(1, h->L);
@@ -2631,13 +2966,17 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     // one buffer for the network: [vaf | leaf_static | static_ok | cand | ncand]
     const size_t o_ls = vp.size() * sizeof(double), o_sok = o_ls + lstat.size() * sizeof(double);
     const size_t o_cand = o_sok + sok.size() * sizeof(uint4), o_ncand = o_cand + cd.size();
-    CKE(ensure(h, h->b_net, o_ncand + nc.size()));
+    const size_t o_desc = o_ncand + nc.size();
+    std::vector<uint8_t> desc(kMaxN, 0);
+    for (int k = 0; k < n; k++) desc[k] = (uint8_t)qof[n - 1 - k];
+    CKE(ensure(h, h->b_net, o_desc + desc.size()));
     char *nb = static_cast<char *>(h->b_net.p);
     CKD(cudaMemcpyAsync(nb, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_ls, lstat.data(), lstat.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_sok, sok.data(), sok.size() * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
     CKD(cudaMemcpyAsync(nb + o_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
+    CKD(cudaMemcpyAsync(nb + o_desc, desc.data(), desc.size(), cudaMemcpyHostToDevice, h->stream));
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
     h->chunk_max = std::min<long long>(h->cap, 1ll << 21);
@@ -2659,16 +2998,18 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     CKE(ensure(h, h->b_sched, sizeof(Sched)));
     h->h_meta = reinterpret_cast<TopMeta *>(h->h_scan + 1);
     h->h_sched = reinterpret_cast<Sched *>(h->h_meta + 1);
+    h->h_rout = reinterpret_cast<ReplayOut *>(h->h_sched + 1);
     h->narrow = getenv("LICHEE_NO_NARROW") == nullptr;
     for (int i = 0; i < 2; i++) {
         CKE(ensure(h, h->b_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
-        CKE(ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * h->stride));
+        CKE(ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * 2 * h->stride));
     }
     h->net.vaf = reinterpret_cast<const double *>(nb);
     h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
     h->net.leaf_static = reinterpret_cast<const double *>(nb + o_ls);
     h->net.cand = reinterpret_cast<const uint8_t *>(nb + o_cand);
     h->net.ncand = reinterpret_cast<const uint8_t *>(nb + o_ncand);
+    h->net.desc_rows = reinterpret_cast<const uint8_t *>(nb + o_desc);
     h->net.n = n; h->net.S = S; h->net.SP = h->SP; h->net.L = h->L; h->net.stride = h->stride;
     h->net.margin = params->vaf_error_margin;
     h->net.static_both = sboth;
@@ -2694,6 +3035,33 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
         g_ctx.attrs_set[h->device] = true;
     }
+    {
+        // reference-order replay: adjacency lists in ROW space, list order kept
+        std::vector<int> roff(n + 1, 0), ridx;
+        std::vector<int> node_of_row(n, 0);
+        for (int t = 0; t < h->L; t++) node_of_row[t + 1] = h->sigma[t];
+        for (int q = 0; q < n; q++) {
+            for (int v : radj[node_of_row[q]]) ridx.push_back(qof[v]);
+            roff[q + 1] = (int)ridx.size();
+        }
+        h->rlay = replay::make_layout(n, h->SP, (int)ridx.size());
+        h->rblob0.assign(h->rlay.total, 0);
+        replay::init_blob(h->rblob0.data(), h->rlay, roff.data(), ridx.data(), params->max_num_grow_calls, params->max_num_trees);
+        h->rblob_in_smem = (size_t)n * h->SP * sizeof(double) + h->rlay.total <= (size_t)kReplaySmemMax;
+        CKE(ensure(h, h->b_rblob, h->rlay.total));
+        CKE(ensure(h, h->b_rout, 256));
+    }
+    if (h->device >= 0 && h->device < 64) {
+        std::lock_guard<std::mutex> g(g_ctx.mu);
+        if (!g_ctx.attrs2_set[h->device]) {
+            CKD(cudaFuncSetAttribute(replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            const int mx = kMaxN * 64 * (int)sizeof(double) + kMaxN;
+            CKD(cudaFuncSetAttribute(score_ref_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            CKD(cudaFuncSetAttribute(score_ref_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+            g_ctx.attrs2_set[h->device] = true;
+        }
+    }
 #undef CKE
     CKD(cudaStreamSynchronize(h->stream));
 #undef CKD
@@ -2704,8 +3072,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
 int lichee_search_run(lichee_search *h) {
     if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
-    const int rc = h->SP == 32 ? run_search<1>(h, h->prm.part_rank, h->prm.part_count, false)
-                               : run_search<2>(h, h->prm.part_rank, h->prm.part_count, false);
+    const int rc = run_whole(h);
     if (rc == LICHEE_OK) h->ran = true;
     return rc;
 }
@@ -2714,9 +3081,12 @@ int lichee_search_run_slice(lichee_search *h, int32_t slice, int32_t n_slices, i
     if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
     if (n_slices < 1 || slice < 0 || slice >= n_slices) { set_err("slice %d of %d out of range", slice, n_slices); return LICHEE_ERR_INVALID; }
     if (keep_ranked && !h->ran) { set_err("keep_ranked needs an earlier run on this handle"); return LICHEE_ERR_STATE; }
+    if (h->cyclic) { set_err("constraint network has a directed cycle: a sliced (canonical) search needs a DAG"); return LICHEE_ERR_CYCLIC; }
+    if (keep_ranked && h->ref_result) { set_err("keep_ranked: the list on this handle is a reference-order result"); return LICHEE_ERR_STATE; }
     CK(cudaSetDevice(h->device));
+    h->ref_result = false;
     const int rc = h->SP == 32 ? run_search<1>(h, slice, n_slices, keep_ranked != 0) : run_search<2>(h, slice, n_slices, keep_ranked != 0);
-    if (rc == LICHEE_OK) h->ran = true;
+    if (rc == LICHEE_OK) { h->ran = true; h->stats.status |= LICHEE_STATUS_CANONICAL_ORDER; }
     return rc;
 }
 
@@ -2726,8 +3096,10 @@ int lichee_search_clear(lichee_search *h) {
     init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
     CK(cudaGetLastError());
     h->flip = 0;
+    h->ref_result = false;
     h->stats = lichee_search_stats{};
     h->stats.num_grow_calls = 0;
+    h->stats.status = LICHEE_STATUS_CANONICAL_ORDER;
     const int rc = fetch_top(h);
     if (rc == LICHEE_OK) h->ran = true;
     return rc;
@@ -2753,6 +3125,21 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
     if (k < 0 || (size_t)k >= h->h_top.size()) { set_err("tree index %d out of range", k); return LICHEE_ERR_INVALID; }
     if (score) *score = h->h_top[k].score;
     if (seq) *seq = h->h_top[k].seq;
+    if (h->ref_result) {
+        // A = treeNodes (without the root) in the order the nodes joined the tree, B = their parents, as rows
+        const uint8_t *a = h->h_tree.data() + (size_t)k * 2 * h->stride, *bp = a + h->stride;
+        const int W = h->stride >> 2;
+        if (parent) parent[0] = -1;
+        if (order) order[0] = 0;
+        for (int i = 0; i < h->L; i++) {
+            const int qa = a[item_byte(i, W)], qb = bp[item_byte(i, W)];
+            if (qa < 1 || qa > h->L || qb > h->L) { set_err("corrupt tree record: rows %d <- %d at position %d", qa, qb, i); return LICHEE_ERR_STATE; }
+            const int node = h->sigma[qa - 1];
+            if (parent) parent[node] = qb == 0 ? 0 : h->sigma[qb - 1];
+            if (order) order[i + 1] = node;
+        }
+        return LICHEE_OK;
+    }
     const uint8_t *b = h->h_tree.data() + (size_t)k * h->stride;
     // byte item_byte(t) holds the row index q of the parent of sigma[t]; q = 0 root, q = j+1 node sigma[j]
     int par_of[kMaxN];
@@ -2803,6 +3190,7 @@ int64_t lichee_record_bytes(const lichee_search *h) { return h ? 24 + h->stride 
 int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_ptr) {
     if (!h || !dst) { set_err("null argument"); return LICHEE_ERR_INVALID; }
     if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
+    if (h->ref_result) { set_err("export_ranked: the list is a reference-order result (one sequential search); shard with part_count > 1 or ref_order_budget < 0"); return LICHEE_ERR_STATE; }
     CK(cudaSetDevice(h->device));
     const long long rb = 24 + h->stride;
     unsigned char *d = nullptr;
@@ -2825,6 +3213,7 @@ int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_pt
 int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_lists, int device_ptr) {
     if (!h || !records || n_lists < 1) { set_err("invalid argument"); return LICHEE_ERR_INVALID; }
     if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
+    if (h->ref_result) { set_err("merge_ranked: the list on this handle is a reference-order result"); return LICHEE_ERR_STATE; }
     CK(cudaSetDevice(h->device));
     const long long rb = 24 + h->stride;
     const long long n = (long long)n_lists * h->prm.num_save;

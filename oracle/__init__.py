@@ -55,13 +55,14 @@ def search(adj, vaf, margin, top_s=1, max_trees=100000, max_grow=100000000, mode
     stats = np.zeros(4, dtype=np.int64)
     alls = np.zeros(max(want_all, 1), dtype=np.float64)
     allp = np.zeros((max(want_all, 1), n), dtype=np.int32)
+    allo = np.zeros((max(want_all, 1), n), dtype=np.int32)
     P = ctypes.c_void_p
     lib.lichee_oracle_search(
         ctypes.c_int(n), ctypes.c_int(S), P(off.ctypes.data), P(idx.ctypes.data), P(vaf.ctypes.data),
         ctypes.c_double(margin), ctypes.c_long(max_trees), ctypes.c_long(max_grow), ctypes.c_int(mode),
         ctypes.c_int(top_s), P(sc.ctypes.data), P(par.ctypes.data), P(order.ctypes.data), P(dfs.ctypes.data),
         P(stats.ctypes.data), P(alls.ctypes.data if want_all else None), P(allp.ctypes.data if want_all else None),
-        ctypes.c_long(want_all))
+        ctypes.c_long(want_all), P(allo.ctypes.data if want_all else None))
     m = int(min(stats[0], top_s))
     out = dict(scores=sc[:m], parents=par[:m], orders=order[:m], dfs_index=dfs[:m], n_trees=int(stats[0]),
                n_grow=int(stats[1]), n_checks=int(stats[2]), stopped=bool(stats[3]))
@@ -69,6 +70,7 @@ def search(adj, vaf, margin, top_s=1, max_trees=100000, max_grow=100000000, mode
         k = int(min(stats[0], want_all))
         out["all_scores"] = alls[:k]
         out["all_parents"] = allp[:k]
+        out["all_orders"] = allo[:k]
     return out
 
 

@@ -256,12 +256,13 @@ static void merge_sort(ranked_t *a, ranked_t *tmp, long n) { /* stable, like Col
  * Outputs hold the first min(top_s, trees) trees of the ranked list: score, parent[n],
  * order[n] = treeNodes (root first, then nodes in the order they joined the tree),
  * dfs_index = position in spanningTrees before sorting.
- * all_scores (may be NULL): scores of every tree in enumeration order, up to all_cap.
+ * all_scores / all_parents / all_orders (may be NULL): score, parents and treeNodes of every tree in
+ * enumeration (discovery) order, up to all_cap trees.
  */
 int lichee_oracle_search(int n, int S, const int *adj_off, const int *adj_idx, const double *vaf,
                          double margin, long max_trees, long max_grow, int mode, int top_s,
                          double *out_score, int *out_parent, int *out_order, long *out_dfs_index,
-                         long *stats, double *all_scores, int *all_parents, long all_cap) {
+                         long *stats, double *all_scores, int *all_parents, long all_cap, int *all_orders) {
     search_t s; memset(&s, 0, sizeof(s));
     s.n = n; s.S = S; s.vaf = vaf; s.margin = margin; s.max_trees = max_trees; s.max_grow = max_grow; s.mode = mode;
     s.adj = (int **)malloc(sizeof(int *) * n); s.adj_len = (int *)calloc(n, sizeof(int));
@@ -284,6 +285,7 @@ int lichee_oracle_search(int n, int S, const int *adj_off, const int *adj_idx, c
         r[i].score = score_tree(&s, s.res_nodes + i * n, s.res_parent + i * n); r[i].idx = i;
         if (all_scores && i < all_cap) all_scores[i] = r[i].score;
         if (all_parents && i < all_cap) memcpy(all_parents + i * n, s.res_parent + i * n, sizeof(int) * n);
+        if (all_orders && i < all_cap) memcpy(all_orders + i * n, s.res_nodes + i * n, sizeof(int) * n);
     }
     merge_sort(r, tmp, s.num_trees);
     long m = s.num_trees < top_s ? s.num_trees : top_s;

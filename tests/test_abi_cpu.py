@@ -39,9 +39,12 @@ def test_struct_layouts_match_the_header(built):
 
 def test_argument_validation_needs_no_gpu(built):
     import lichee_b200
-    with pytest.raises(lichee_b200.LicheeError) as e:            # directed cycle 1 -> 2 -> 1
-        lichee_b200.LineageSearch([[1], [2], [1]], np.array([[0.5], [0.3], [0.2]]))
-    assert e.value.code == -3
+    with pytest.raises(lichee_b200.LicheeError) as e:            # NaN centroid
+        lichee_b200.LineageSearch([[1], []], np.array([[0.5], [float("nan")]]))
+    assert e.value.code == -1
+    with pytest.raises(lichee_b200.LicheeError) as e:            # adjacency lists / matrix disagree
+        lichee_b200.LineageSearch([[1], [], []], np.array([[0.5], [0.2]]))
+    assert e.value.code == -1
     with pytest.raises(lichee_b200.LicheeError) as e:            # too many samples
         lichee_b200.LineageSearch([[1], []], np.zeros((2, 65)))
     assert e.value.code == -4
@@ -69,6 +72,6 @@ def test_product_package_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "lichee_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "lichee_oracle" not in txt, f

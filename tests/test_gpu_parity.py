@@ -40,7 +40,10 @@ def rand_dag(rng, n, S, p_edge, vaf_scale):
 
 
 def gpu_search(adj, vaf, margin, num_save, **kw):
+    """Canonical-order search unless the caller passes ref_order_budget (tests/test_gpu_reference_order.py
+    covers the reference-order mode)."""
     import lichee_b200
+    kw.setdefault("ref_order_budget", -1)
     s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=num_save, **kw)
     try:
         st = s.run()
@@ -163,7 +166,8 @@ def test_edge_cases(built):
     # duplicate edges collapse (PHYNetwork.addEdge refuses duplicates)
     st, trees, _ = gpu_search([[1, 1, 2], [2], []], np.array([[0.5], [0.3], [0.2]]), 0.1, 5)
     assert st["num_trees"] == 2
-    # a directed cycle is rejected
+    # a directed cycle: the canonical parent-choice search needs a DAG (the reference-order replay does not,
+    # tests/test_gpu_reference_order.py)
     with pytest.raises(lichee_b200.LicheeError) as e:
         gpu_search([[1], [2], [1]], np.array([[0.5], [0.3], [0.2]]), 0.1, 1)
     assert e.value.code == -3
@@ -241,7 +245,7 @@ def test_work_stealing_slices_give_the_whole_search(built):
     net, prm = make_instance(11, 5, seed=4)
     whole, trees, _ = gpu_search(net.adj, net.aaf, prm.vaf_error_margin, 40, max_num_trees=10**9)
     T = 12
-    s = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
+    s = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
     todo = iter(range(T + 1))
     assert s.run_claimed(T, lambda: next(todo))
     st = s.stats()
@@ -250,9 +254,9 @@ def test_work_stealing_slices_give_the_whole_search(built):
     assert [t.parent for t in got] == [t.parent for t in trees]
     assert [t.errorScore for t in got] == [t.errorScore for t in trees]
     s.close()
-    a = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
-    b = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
-    c = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9)
+    a = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
+    b = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
+    c = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
     order_a, order_b = iter([11, 0, 5, 7, 2, T]), iter([3, 10, 1, 9, 8, 6, 4, T])
     a.run_claimed(T, lambda: next(order_a))
     b.run_claimed(T, lambda: next(order_b))
@@ -277,7 +281,7 @@ def test_full_size_properties(built, n_clusters, n_samples, cap):
     import lichee_b200
     net, prm = make_instance(n_clusters, n_samples, seed=2026)
     vaf = np.array(net.aaf)
-    s = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap)
+    s = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap, ref_order_budget=-1)
     st = s.run()
     trees = s.trees()
     assert st.num_trees == cap and st.num_scored == cap and (st.status & 1)
@@ -295,14 +299,14 @@ def test_full_size_properties(built, n_clusters, n_samples, cap):
     assert again.num_trees == st.num_trees and [t.parent for t in s.trees()] == [t.parent for t in trees]   # idempotent
     s.close()
     small = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap,
-                                      level_capacity=1 << 16)
+                                      level_capacity=1 << 16, ref_order_budget=-1)
     st2 = small.run()
     t2 = small.trees()
     assert st2.num_trees == cap and st2.num_launches > st.num_launches
     assert [(t.errorScore, t.seq, t.parent) for t in t2] == [(t.errorScore, t.seq, t.parent) for t in trees]
     small.close()
     # a tighter prefix cap keeps exactly the trees of the longer run whose seq is below it
-    half = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap // 4)
+    half = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=1000, max_num_trees=cap // 4, ref_order_budget=-1)
     half.run()
     th = half.trees()
     best_possible = sorted((t.errorScore, t.seq) for t in trees if t.seq < cap // 4)
