@@ -7,7 +7,17 @@ the reference's own edge rule under -c (complete edges), -minClusterSize 1, -e 0
 One "step" = one whole tree search of that network: enumerate spanning trees in canonical order,
 sum-rule check every candidate extension, score every complete valid tree, keep the top 1000.
 Parameters.MAX_NUM_TREES is raised from the reference's 100000 to --max-trees so that a step is
-long enough to measure a B200 (with the reference's default a step is ~10 ms of launch latency).
+long enough to measure a B200 (with the reference's default a step is ~1 ms of launch latency).
+The step runs in CANONICAL order (ref_order_budget = -1): the library's default reference-order replay
+cannot finish on this network -- the literal port of the reference needs its full 10^8 grow() calls and
+finds no tree (tests/golden/reference_caps.json) -- so the default mode would fall back to exactly this
+search after spending its replay budget.  The reference-order mode is measured on the networks where the
+reference itself finishes: `bundled_datasets_build_search_ms` (identical output, checked in the run).
+
+  top_list_sha256     : digest of the ranked top-s list; every timed step must produce the same one, and the
+                        120x64 / 40x20 digests at the default cap are pinned in tests/golden/canonical_digests.json
+  same_output_baseline: the sequential canonical specification (CPU, one core) on the same network with the same
+                        caps, output bit-identical (digests compared in the run), next to the GPU end-to-end time
 
   value : candidate extensions checked per second, whole job, network already resident in HBM
   e2e   : same, through the public API with HOST buffers: create (H2D) + run + ranked trees D2H
@@ -96,9 +106,11 @@ class ClockSampler:
 
 def bundled_search_times(lichee_b200, with_cpu):
     """-build search wall time on the bundled ccRCC / HGSC networks (BASELINE configs[0..2], README
-    settings, committed fixtures): end to end through the public API from host arrays, median of 5,
-    next to the CPU port of the reference search.  These searches are a handful of trees: they
-    measure launch latency, not throughput."""
+    settings, committed fixtures): end to end through the public API from host arrays, median of 5, in the
+    library's DEFAULT mode (reference order: replay + reference-order scoring) and in canonical mode, next to
+    the CPU port of the reference search; `identical` = ranked list (scores bit for bit, parents, treeNodes
+    order) equal to the literal port's, checked here.  These searches are a handful of trees: they measure
+    launch latency, not throughput."""
     path = os.path.join(ROOT, "tests", "golden", "networks_bundled.json")
     if not os.path.exists(path):
         return None
@@ -107,19 +119,65 @@ def bundled_search_times(lichee_b200, with_cpu):
         if e["clustering"] != "single" or e["complete_edges"]:
             continue
         adj, vaf = e["adj"], np.array(e["aaf"])
-        ts = []
-        for _ in range(6):
-            t0 = time.perf_counter()
-            s = lichee_b200.LineageSearch(adj, vaf, e["vaf_error_margin"], num_save=100 if "hgsc" in e["dataset"] else 1)
-            st = s.run(); s.trees(); s.close()
-            ts.append(1e3 * (time.perf_counter() - t0))
-        rec = {"nodes": len(adj), "valid_trees": int(st.num_trees), "gpu_e2e_ms": round(statistics.median(ts[1:]), 3)}
+        save = 100 if "hgsc" in e["dataset"] else 1
+        rec = {"nodes": len(adj)}
+        for mode, budget in (("gpu_e2e_ms", 0), ("gpu_canonical_e2e_ms", -1)):
+            ts = []
+            for _ in range(6):
+                t0 = time.perf_counter()
+                s = lichee_b200.LineageSearch(adj, vaf, e["vaf_error_margin"], num_save=save, ref_order_budget=budget)
+                st = s.run(); trees = s.trees(); s.close()
+                ts.append(1e3 * (time.perf_counter() - t0))
+            rec[mode] = round(statistics.median(ts[1:]), 3)
+            if budget == 0:
+                rec["valid_trees"] = int(st.num_trees)
+                rec["grow_calls"] = int(st.num_grow_calls)
+                rec["reference_order"] = not (st.status & lichee_b200.STATUS_CANONICAL_ORDER)
+                ref_trees = trees
         if with_cpu:
             import oracle
             t0 = time.perf_counter()
-            oracle.search(adj, vaf, e["vaf_error_margin"], top_s=100)
+            r = oracle.search(adj, vaf, e["vaf_error_margin"], top_s=save)
             rec["cpu_port_ms"] = round(1e3 * (time.perf_counter() - t0), 3)
+            rec["identical"] = bool(len(ref_trees) == len(r["scores"]) and
+                                    all(t.errorScore == r["scores"][k] and t.parent == list(r["parents"][k]) and
+                                        t.treeNodes == list(r["orders"][k]) for k, t in enumerate(ref_trees)))
         out[e["dataset"]] = rec
+    return out
+
+
+def same_output_baseline(lichee_b200, args):
+    """The sequential canonical specification (oracle/, one core) against the GPU on the SAME network with the
+    SAME caps (the reference's defaults: MAX_NUM_TREES 100000), output bit-identical: the clean GPU-vs-CPU ratio
+    for identical work.  The literal reference port is beside it for scale: it is a different traversal
+    (tests/golden/reference_caps.json: 40x20 reaches the cap after 3.5e7 grow() calls / 57 s, 120x64 finds no tree
+    in 10^8 calls / 976 s)."""
+    import oracle
+    from lichee_b200.synth import make_instance
+    out = {}
+    for (c, smp, save) in ((120, 64, 1000), (40, 20, 1000)):
+        net, prm = make_instance(c, smp, seed=args.seed)
+        vaf = np.ascontiguousarray(net.aaf, dtype=np.float64)
+        t0 = time.perf_counter()
+        r = oracle.canonical_search(net.adj, vaf, prm.vaf_error_margin, top_s=save, max_trees=100000)
+        cpu_s = time.perf_counter() - t0
+        import hashlib
+        hh = hashlib.sha256()
+        hh.update(np.ascontiguousarray(r["scores"], dtype=np.float64).tobytes())
+        hh.update(np.ascontiguousarray(r["seq"], dtype=np.int64).tobytes())
+        hh.update(np.ascontiguousarray(r["parents"], dtype=np.int32).tobytes())
+        ts, digest = [], None
+        for _ in range(6):
+            t0 = time.perf_counter()
+            s = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=save, max_num_trees=100000, ref_order_budget=-1)
+            st = s.run(); trees = s.trees(); s.close()
+            ts.append(time.perf_counter() - t0)
+            digest = lichee_b200.top_list_sha256(trees)
+        gpu_s = statistics.median(ts[1:])
+        out[f"{c}x{smp} default caps (-s {save})"] = {
+            "valid_trees": int(st.num_trees), "cpu_canonical_spec_ms": round(1e3 * cpu_s, 3), "cpu_cores": 1,
+            "gpu_e2e_ms": round(1e3 * gpu_s, 3), "ratio": round(cpu_s / gpu_s, 1), "top_list_sha256": digest,
+            "identical": digest == hh.hexdigest()}
     return out
 
 
@@ -133,7 +191,8 @@ def named_shape_times(lichee_b200, adj, vaf, margin, args):
         ts, st = [], None
         for _ in range(6):
             t0 = time.perf_counter()
-            s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=save, max_num_trees=max_trees, max_num_grow_calls=max_grow)
+            s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=save, max_num_trees=max_trees, max_num_grow_calls=max_grow,
+                                          ref_order_budget=-1)
             st = s.run(); s.trees(); s.close()
             ts.append(1e3 * (time.perf_counter() - t0))
         return {"e2e_ms": round(statistics.median(ts[1:]), 3), "valid_trees": int(st.num_trees), "checks": int(st.num_checks),
@@ -171,7 +230,12 @@ def run_reference(args):
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "clusters": args.clusters, "samples": args.samples, "edges": n_edges,
-                   "seed": args.seed, "num_save": args.save},
+                   "seed": args.seed, "num_save": args.save, "max_num_trees_per_gpu": args.max_trees,
+                   "parallelism": "single host thread (the reference search is single-threaded)",
+                   "order": "the reference's own Gabow-Myers traversal; a bounded sample of it per step: the full search "
+                            "of this network runs into MAX_NUM_GROW_CALLS = 10^8 without a valid tree (976 s, "
+                            "tests/golden/reference_caps.json)",
+                   "valid_trees_per_step": int(r["n_trees"])},
         "cpu_baseline": {"value": val, "unit": "candidate trees/s", "cores": 1, "kind": "port",
                          "sample": f"first {sample_grow} grow() calls of the reference's Gabow-Myers search per step "
                                    f"(literal C port of PHYNetwork.grow; the search is single-threaded in the reference; no JVM in this image)"},
@@ -216,7 +280,7 @@ def main():
 
     adj, vaf, margin, n_edges = make_workload(args)
     kw = dict(num_save=args.save, max_num_trees=args.max_trees, max_num_grow_calls=1 << 62, device=local,
-              part_rank=rank, part_count=world, level_capacity=args.level_capacity)
+              part_rank=rank, part_count=world, level_capacity=args.level_capacity, ref_order_budget=-1)
 
     # pinned host staging of the step's inputs (the arrays the Java host would hand over)
     off = np.zeros(len(adj) + 1, dtype=np.int32)
@@ -267,6 +331,7 @@ def main():
     barrier()
     t_dev = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
+    digests = {lichee_b200.top_list_sha256(resident.trees())}
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -275,17 +340,25 @@ def main():
     e2e_out = [step_e2e() for _ in range(args.steps)]
     barrier()
     t_e2e = time.perf_counter() - t0
+    digests |= {lichee_b200.top_list_sha256(trees) for _, trees in e2e_out}
+    if len(digests) != 1:
+        raise SystemExit(f"bench.py: the timed steps disagree on the ranked list: {sorted(digests)}")
+    top_digest = digests.pop()
 
     checks = sum(s.num_checks for s in stats)
     scored = sum(s.num_scored for s in stats)
+    evaluated = sum(s.num_evaluated for s in stats)
+    leaf_items = sum(s.num_leaf_items for s in stats)
+    bounded_items = sum(s.num_bounded_items for s in stats)
     launches = sum(s.num_launches for s in stats) + (args.steps * 3 if world > 1 else 0)
-    agg = torch.tensor([float(checks), float(scored), float(launches), float(sum(s.num_checks for s, _ in e2e_out))],
+    agg = torch.tensor([float(checks), float(scored), float(launches), float(sum(s.num_checks for s, _ in e2e_out)),
+                        float(evaluated), float(leaf_items), float(bounded_items)],
                        dtype=torch.float64, device="cuda")
     tmax = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(agg)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    checks_all, scored_all, launches_all, e2e_checks_all = [float(x) for x in agg.tolist()]
+    checks_all, scored_all, launches_all, e2e_checks_all, eval_all, leaf_all, bounded_all = [float(x) for x in agg.tolist()]
     t_dev, t_e2e = [float(x) for x in tmax.tolist()]
 
     if rank == 0:
@@ -315,8 +388,18 @@ def main():
                        "parallelism": f"frontier slices x{world}" if world > 1 else "single GPU",
                        "l2": "frontier chunks are produced and consumed once per step; every level buffer is rewritten "
                              "between timed steps (working set of a step > 126 MB L2)",
+                       "order": "canonical (ref_order_budget=-1): the reference-order replay cannot finish on this network "
+                                "(literal port: 10^8 grow() calls, 0 valid trees, 976 s; tests/golden/reference_caps.json)",
                        "valid_trees_per_step": st0.num_trees * world if world > 1 else st0.num_trees,
                        "complete_trees_scored_per_s": scored_all / t_dev},
+            "top_list_sha256": top_digest,
+            "what_value_counts": "sum-rule DECISIONS per second (one per candidate extension, what the reference decides with one "
+                                 "checkConstraint call); most are carried over from the lexicographic neighbour, read from a "
+                                 "precomputed bit, or belong to items dismissed by the lower bound -- see the three rates below",
+            "valid_trees_ranked_per_s": scored_all / t_dev,
+            "evaluated_trees_per_s": eval_all / t_dev,
+            "bounded_fraction": {"last_level_items": bounded_all / max(leaf_all, 1.0),
+                                 "valid_trees": 1.0 - eval_all / max(scored_all, 1.0)},
             "e2e": {"value": e2e_checks_all / t_e2e, "unit": "candidate trees/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches_all),
@@ -337,8 +420,24 @@ def main():
                       "CUDA events on the library's own stream (rank 0)",
         }
         if world == 1:
+            # the same search with the lower bound switched off: every valid tree is scored
+            os.environ["LICHEE_NO_PRUNE"] = "1"
+            nop = lichee_b200.LineageSearch(adj, vaf, margin, **dict(kw, max_num_trees=min(args.max_trees, 1 << 28)))
+            del os.environ["LICHEE_NO_PRUNE"]
+            nop.run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nst = nop.run()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            nop.close()
+            line["no_prune"] = {"max_num_trees": min(args.max_trees, 1 << 28), "ms_per_step": 1e3 * dt,
+                                "evaluated_trees_per_s": nst.num_evaluated / dt, "checks_per_s": nst.num_checks / dt,
+                                "note": "LICHEE_NO_PRUNE=1: same search, lower bound off, every valid tree scored"}
             line["bundled_datasets_build_search_ms"] = bundled_search_times(lichee_b200, not args.no_cpu_baseline)
             line["named_shapes"] = named_shape_times(lichee_b200, adj, vaf, margin, args)
+            if not args.no_cpu_baseline:
+                line["same_output_baseline"] = same_output_baseline(lichee_b200, args)
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             t0 = time.perf_counter()

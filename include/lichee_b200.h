@@ -107,6 +107,11 @@ typedef struct lichee_search_stats {
     int64_t kernel_bytes[LICHEE_NUM_KERNELS];
     uint32_t status;
     uint32_t num_saved;          /* trees held in the ranked list, <= num_save                  */
+    int64_t num_evaluated;       /* complete valid trees whose error score was actually computed (canonical
+                                    search: num_scored minus the trees dismissed by the lower bound of their
+                                    base; reference order: every recorded tree)                   */
+    int64_t num_bounded_items;   /* last-level frontier items skipped by the lower bound         */
+    int64_t num_leaf_items;      /* last-level frontier items in total                           */
 } lichee_search_stats;
 
 void lichee_default_params(lichee_search_params *p);

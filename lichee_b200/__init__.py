@@ -51,7 +51,8 @@ class SearchStats(ctypes.Structure):
                 ("num_launches", ctypes.c_int64), ("frontier_bytes", ctypes.c_int64),
                 ("kernel_ms_total", ctypes.c_double), ("kernel_ms", ctypes.c_double * 5),
                 ("kernel_launches", ctypes.c_int64 * 5), ("kernel_bytes", ctypes.c_int64 * 5),
-                ("status", ctypes.c_uint32), ("num_saved", ctypes.c_uint32)]
+                ("status", ctypes.c_uint32), ("num_saved", ctypes.c_uint32),
+                ("num_evaluated", ctypes.c_int64), ("num_bounded_items", ctypes.c_int64), ("num_leaf_items", ctypes.c_int64)]
 
     KERNELS = ("check", "scan", "emit", "leaf", "select")
 
@@ -178,6 +179,17 @@ class PHYTree:
         return "".join(f"{p} -> {c}\n" for p in sorted(self.treeEdges) for c in self.treeEdges[p])
 
     __str__ = toString
+
+
+def top_list_sha256(trees):
+    """SHA-256 of a ranked list: scores (f64) | seq (i64) | parents (i32), ranked order.  bench.py prints it for
+    every step and tests/golden/canonical_digests.json pins it for the benched shapes."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.array([t.errorScore for t in trees], dtype=np.float64).tobytes())
+    h.update(np.array([t.seq for t in trees], dtype=np.int64).tobytes())
+    h.update(np.array([t.parent for t in trees], dtype=np.int32).tobytes())
+    return h.hexdigest()
 
 
 class LineageSearch:

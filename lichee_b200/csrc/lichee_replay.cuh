@@ -18,7 +18,7 @@
 //                               psum[k] = psum[lastchild[p]] + VAF(tn[k])  (0.0 + VAF for a first child),
 //                               the same left-to-right double additions as PHYTree.java:162-165
 //   this.edges (adjacency)      adj[u][0..adjlen[u]) in list order; removeEdge shifts, addEdge appends
-//   f (ArrayList used as stack) fs[0..top) with tombstones; pos[u*n+v] = index of edge (u,v) in fs or
+//   f (ArrayList used as stack) fs[0..top) with tombstones; pos[v*n+u] = index of edge (u,v) in fs or
 //                               kNone.  Order of the live entries == order of the ArrayList.
 //   edgesRemoved / ff           slices of two stacks (an edge sits in at most one frame's list)
 //   edgesAdded                  not stored: when grow() returns, the edges of f that leave v are exactly
@@ -31,10 +31,16 @@
 //                               further tree can be recorded (a tree is only recorded at the top of a
 //                               grow() call and no further call is made), so the replay simply stops
 //
-// The same source compiles for the device (lane 0 of one warp runs the transitions; the warp's lanes
-// split the per-sample work of the sum rule and the words of a recorded tree) and for the host (tests/replay_harness.cpp: the algorithm against the literal
-// restatement in oracle/, on the CPU, thousands of instances).  The host build is a test of this
-// source, not a code path of the library.
+// Two statements of the same machine over the same state blob (Layout / Header / init_blob below):
+//   * step()            the sequential statement, one thread.  tests/harness/replay_harness.cpp compiles it for
+//                       the HOST and tests/test_replay_cpu.py fuzzes it against the literal restatement of
+//                       PHYNetwork.grow in oracle/ (thousands of digraphs, both caps, pause/resume).  It is test
+//                       infrastructure and documentation: the library has no host path.
+//   * replay_kernel     (lichee_search.cu) the warp statement the device runs: the 32 lanes execute the same
+//                       transitions with the scalars in registers and split every list scan -- the adjacency list
+//                       of v, the edges into v, the restored / re-appended edge lists, the samples of the sum rule,
+//                       the words of a recorded tree -- with ballots.  tests/test_gpu_reference_order.py checks it
+//                       against the same literal restatement on the GPU.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -136,6 +142,9 @@ RP_HD State bind(unsigned char *blob, const Layout &L) {
     return s;
 }
 
+// pos is indexed by (target, source): the scan for the edges INTO a node reads consecutive entries
+RP_HD int pos_index(int n, int u, int v) { return v * n + u; }
+
 // Initial state of getLineageTrees() (PHYNetwork.java:547-565): t = {root}, f = the root's edges in
 // adjacency order.  adj_off/adj_idx: adjacency lists in ROW space, list order kept; the caller has dropped
 // duplicates (addEdge refuses them), self loops and edges into the root (the root is in t from the start,
@@ -164,7 +173,7 @@ inline void init_blob(unsigned char *blob, const Layout &L, const int *adj_off, 
     for (int i = 0; i < s.adjlen[0]; i++) {
         const int w = s.adj[i];
         s.fs[h->top] = (uint16_t)(w);                    // code of (0, w) = 0 << 7 | w
-        s.pos[w] = (uint16_t)h->top;
+        s.pos[pos_index(n, 0, w)] = (uint16_t)h->top;
         h->top++; h->f_live++;
     }
     h->phase = P_ENTER; h->depth = 0;
@@ -181,7 +190,7 @@ RP_HD void compact(State &s) {                           // squeeze the tombston
         const uint16_t c = s.fs[i];
         if (c != kNone) {
             s.fs[k] = c;
-            s.pos[(c >> 7) * s.n + (c & 127)] = (uint16_t)k;
+            s.pos[pos_index(s.n, c >> 7, c & 127)] = (uint16_t)k;
             k++;
         }
     }
@@ -193,16 +202,16 @@ RP_HD void push_edge(State &s, uint16_t code) {          // f.add(e)
     Header *h = s.h;
     if (h->top == s.fs_cap) compact(s);
     s.fs[h->top] = code;
-    s.pos[(code >> 7) * s.n + (code & 127)] = (uint16_t)h->top;
+    s.pos[pos_index(s.n, code >> 7, code & 127)] = (uint16_t)h->top;
     h->top++;
     h->f_live++;
 }
 
 RP_HD void kill_edge(State &s, int u, int v) {           // remove edge (u,v) from f if it is there
-    const uint16_t p = s.pos[u * s.n + v];
+    const uint16_t p = s.pos[pos_index(s.n, u, v)];
     if (p != kNone) {
         s.fs[p] = kNone;
-        s.pos[u * s.n + v] = kNone;
+        s.pos[pos_index(s.n, u, v)] = kNone;
         s.h->f_live--;
     }
 }
@@ -250,7 +259,7 @@ RP_HD Result step(State &s, bool room) {
         h->top = top;
         h->f_live--;
         const int u = code >> 7, v = code & 127;
-        s.pos[u * n + v] = kNone;
+        s.pos[pos_index(n, u, v)] = kNone;
         s.fu[d] = (uint8_t)u; s.fv[d] = (uint8_t)v;
         const int k = h->tcount;                         // t.addNode(v); t.addEdge(u, v)
         const uint8_t prev = s.last[u];
@@ -281,18 +290,18 @@ RP_HD Result step(State &s, bool room) {
                 const int b = RP_CTZ(m);
                 m &= m - 1;
                 const int w = g * 32 + b;
-                const uint16_t p = s.pos[w * n + v];
+                const uint16_t p = s.pos[pos_index(n, w, v)];
                 if (p == kNone) continue;
                 int j = cnt;                             // insertion sort by position in f
-                while (j > 0 && s.pos[(s.rem[base + j - 1] >> 7) * n + v] > p) { s.rem[base + j] = s.rem[base + j - 1]; j--; }
+                while (j > 0 && s.pos[pos_index(n, s.rem[base + j - 1] >> 7, v)] > p) { s.rem[base + j] = s.rem[base + j - 1]; j--; }
                 s.rem[base + j] = (uint16_t)((w << 7) | v);
                 cnt++;
             }
         }
         for (int j = 0; j < cnt; j++) {
             const int w = s.rem[base + j] >> 7;
-            s.fs[s.pos[w * n + v]] = kNone;
-            s.pos[w * n + v] = kNone;
+            s.fs[s.pos[pos_index(n, w, v)]] = kNone;
+            s.pos[pos_index(n, w, v)] = kNone;
         }
         h->f_live -= cnt;
         h->rem_top = base + cnt;

@@ -116,6 +116,7 @@ struct TopMeta {             // device-resident state of the ranked list
     unsigned long long n_valid; // valid complete trees counted by the current leaf launch
     unsigned long long next_run; // work queue of the current leaf launch: next unclaimed run of items
     unsigned long long n_bounded; // items of the current leaf launch whose trees were excluded by the lower bound
+    unsigned long long n_eval;   // trees of the current leaf launch whose total was computed
 };
 
 struct ScanOut {             // written by the scan, read back by the host once per chunk
@@ -1182,7 +1183,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     bool full;
     double tau;
     const double tmax = admit_bound(meta, num_save, full, tau);
-    unsigned long long my_valid = 0;
+    unsigned long long my_valid = 0, my_eval = 0;
     unsigned my_bounded = 0;
     // candidate slots are reserved kCandBatch at a time per warp (one atomic on the shared counter per batch,
     // not per tree: in a good region millions of trees beat a stale threshold within one launch); slots a
@@ -1366,6 +1367,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
         // Base reduction over the 128 slots, remembering what each lane received at every stage: a
         // tree differs from the base in one slot of one lane, so its total is that lane's partial
         // pushed through the same five additions -- bit-identical to a full butterfly.
+        my_eval += __popc(pq0) + __popc(pq1) + __popc(pq2) + __popc(pq3);
         const double P = __dadd_rn(__dadd_rn(E0, E1), __dadd_rn(E2, E3));
         double rcv[5];
         {
@@ -1431,6 +1433,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     for (int d = 16; d > 0; d >>= 1) my_valid += __shfl_xor_sync(kFull, my_valid, d);
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
     if (lane == 0 && my_bounded) atomicAdd(&meta->n_bounded, (unsigned long long)my_bounded);
+    if (lane == 0 && my_eval) atomicAdd(&meta->n_eval, my_eval);
 }
 
 // Gives every candidate its canonical sequence number (rank among the valid trees) now that the
@@ -1624,7 +1627,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
         meta->n_valid = 0;
-        meta->next_run = 0; meta->n_bounded = 0;
+        meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
     }
 }
 
@@ -1731,7 +1734,7 @@ radix_compact(const Cand *__restrict__ cands, long long m, RadixState *st, Cand 
     }
 }
 
-__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; }
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -1739,7 +1742,7 @@ __global__ void init_meta(TopMeta *meta) {
     meta->tau = INFINITY;
     meta->n_cand = 0;
     meta->n_valid = 0;
-    meta->next_run = 0; meta->n_bounded = 0;
+    meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
 }
 
 // unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
@@ -1825,68 +1828,273 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
     }
     __syncthreads();
     if (threadIdx.x < 32) {
+        // The warp statement of the machine in lichee_replay.cuh (step() there is the sequential statement).
+        // All 32 lanes run the same transitions; the scalars of the Header live in registers, identical in
+        // every lane; arrays are written by lane 0 (single elements) or by the lanes that own an element of a
+        // list scan; a __syncwarp() separates every write from a read by another lane.
+        using namespace replay;
         const int lane = threadIdx.x;
-        replay::State s = replay::bind(blob, lay);
-        replay::Header *h = s.h;
-        const bool valid0 = lane < S, valid1 = SPL == 2 && lane + 32 < S;
+        const unsigned lt = (1u << lane) - 1u;
+        State s = bind(blob, lay);
+        const int n = lay.n;
         const int W = stride >> 2;
+        const bool valid0 = lane < S, valid1 = SPL == 2 && lane + 32 < S;
+        long long num_grow = s.h->num_grow, num_checks = s.h->num_checks, num_trees = s.h->num_trees;
+        long long compactions = s.h->compactions;
+        const long long max_grow = s.h->max_grow, max_trees = s.h->max_trees;
+        int top = s.h->top, f_live = s.h->f_live, ff_top = s.h->ff_top, rem_top = s.h->rem_top;
+        int depth = s.h->depth, tcount = s.h->tcount, phase = s.h->phase, status = s.h->status;
+        unsigned t0 = s.h->inT[0], t1 = s.h->inT[1], t2 = s.h->inT[2], t3 = s.h->inT[3];
+        const long long grow_start = num_grow;
         int rec_count = 0;
-        long long steps = 0;
-        for (;;) {
-            int r = replay::R_STOP;
-            if (lane == 0) {
-                // transitions up to the next piece of warp work
-                while (steps < step_quota && h->num_grow < grow_limit) {
-                    steps++;
-                    r = replay::step(s, rec_count < rec_cap);
-                    if (r != replay::R_CONTINUE) break;
-                }
-                if (r == replay::R_CONTINUE) r = replay::R_STOP;     // quota or budget used up between two transitions
-            }
+        auto tword = [&](int g) { return g == 0 ? t0 : g == 1 ? t1 : g == 2 ? t2 : t3; };
+        auto in_t = [&](int v) { return (tword(v >> 5) >> (v & 31)) & 1u; };
+        auto compact = [&]() {                           // squeeze the tombstones out of fs
             __syncwarp();
-            r = __shfl_sync(kFull, r, 0);
-            if (r == replay::R_STOP) break;
-            if (r == replay::R_CHECK) {
-                // t.checkConstraint(u) with v appended (PHYTree.java:156-174): running sum of u's children
-                const int u = h->cu, v = h->cv, k = h->ck, prev = h->cprev;
-                double x0, x1, a0, a1, p0 = 0.0, p1 = 0.0;
-                load_row<SPL>(vaf_s, v, SP, lane, x0, x1);
-                load_row<SPL>(vaf_s, u, SP, lane, a0, a1);
-                if (prev != replay::kNoChild) load_row<SPL>(s.psum, prev, SP, lane, p0, p1);
-                const double s0 = __dadd_rn(p0, x0), s1 = __dadd_rn(p1, x1);
-                if (SPL == 2) reinterpret_cast<double2 *>(s.psum)[k * 32 + lane] = make_double2(s0, s1);
-                else s.psum[k * SP + lane] = s0;
-                bool bad = valid0 && s0 > __dadd_rn(a0, margin);
-                if (SPL == 2) bad |= valid1 && s1 > __dadd_rn(a1, margin);
-                const bool ok = !__any_sync(kFull, bad);
-                if (lane == 0) h->ok = ok ? 1 : 0;
-            } else {                                     // R_RECORD
-                unsigned char *rp = records + (size_t)rec_count * record_bytes;
-                if (lane == 0) {
-                    *reinterpret_cast<double *>(rp) = 0.0;
-                    *reinterpret_cast<long long *>(rp + 8) = h->num_trees;
-                    *reinterpret_cast<int *>(rp + 16) = 0;
-                    *reinterpret_cast<int *>(rp + 20) = 1;
+            int k = 0;
+            for (int base = 0; base < top; base += 32) {
+                const int i = base + lane;
+                const unsigned c = i < top ? s.fs[i] : kNone;
+                const unsigned live = __ballot_sync(kFull, c != kNone);
+                __syncwarp();
+                if (c != kNone) {
+                    const int d = k + __popc(live & lt);
+                    s.fs[d] = (uint16_t)c;
+                    s.pos[pos_index(n, c >> 7, c & 127)] = (uint16_t)d;
                 }
-                if (lane < W) {
-                    unsigned a = 0, b = 0;
-                    for (int q = 3; q >= 0; q--) {
-                        const int i = q * W + lane;      // tree position i <-> treeNodes[i + 1]
-                        unsigned ab = 0xffu, bb = 0xffu;
-                        if (i < L) { ab = s.tn[i + 1]; bb = s.par[ab]; }
-                        a = (a << 8) | ab;
-                        b = (b << 8) | bb;
+                k += __popc(live);
+                __syncwarp();
+            }
+            top = k;
+            compactions++;
+        };
+        auto push_lanes = [&](bool take, unsigned code) {   // f.add(e) for every taking lane, in lane order
+            if (top + 32 > lay.fs_cap) compact();
+            const unsigned m = __ballot_sync(kFull, take);
+            if (take) {
+                const int d = top + __popc(m & lt);
+                s.fs[d] = (uint16_t)code;
+                s.pos[pos_index(n, code >> 7, code & 127)] = (uint16_t)d;
+            }
+            const int c = __popc(m);
+            top += c;
+            f_live += c;
+        };
+        while (status == S_RUNNING) {
+            __syncwarp();
+            if (phase == P_ENTER) {                      // grow(t), PHYNetwork.java:443-449
+                if (num_grow >= grow_limit || num_grow - grow_start >= step_quota) break;   // pause before counting the call
+                if (tcount == n) {
+                    if (rec_count >= rec_cap) break;     // record buffer full: pause
+                    num_grow++;
+                    unsigned char *rp = records + (size_t)rec_count * record_bytes;
+                    if (lane == 0) {
+                        *reinterpret_cast<double *>(rp) = 0.0;
+                        *reinterpret_cast<long long *>(rp + 8) = num_trees;
+                        *reinterpret_cast<int *>(rp + 16) = 0;
+                        *reinterpret_cast<int *>(rp + 20) = 1;
                     }
-                    reinterpret_cast<unsigned *>(rp + 24)[lane] = a;
-                    reinterpret_cast<unsigned *>(rp + 24 + stride)[lane] = b;
+                    if (lane < W) {
+                        unsigned a = 0, b = 0;
+                        for (int q = 3; q >= 0; q--) {
+                            const int i = q * W + lane;  // tree position i <-> treeNodes[i + 1]
+                            unsigned ab = 0xffu, bb = 0xffu;
+                            if (i < L) { ab = s.tn[i + 1]; bb = s.par[ab]; }
+                            a = (a << 8) | ab;
+                            b = (b << 8) | bb;
+                        }
+                        reinterpret_cast<unsigned *>(rp + 24)[lane] = a;
+                        reinterpret_cast<unsigned *>(rp + 24 + stride)[lane] = b;
+                    }
+                    rec_count++;
+                    num_trees++;
+                    if (depth == 0) { status = S_DONE; break; }      // only when the network is the root alone
+                    depth--;
+                    phase = P_AFTER_RETURN;
+                    continue;
                 }
-                rec_count++;
+                num_grow++;
+                if (lane == 0) s.ffbase[depth] = (uint16_t)ff_top;
+                phase = P_LOOP;
             }
-            __syncwarp();
+            if (phase == P_LOOP) {                       // while(!b && f.size() > 0), :454-495
+                if (f_live == 0) { phase = P_FINISH; continue; }
+                unsigned code;
+                for (;;) {                               // pop: the topmost live entry
+                    const int i = top - 1 - lane;
+                    const unsigned c = i >= 0 ? s.fs[i] : kNone;
+                    const unsigned m = __ballot_sync(kFull, c != kNone);
+                    if (m) { const int j = __ffs(m) - 1; code = __shfl_sync(kFull, c, j); top = top - 1 - j; break; }
+                    top -= 32;
+                }
+                f_live--;
+                const int u = code >> 7, v = code & 127;
+                const int k = tcount;                    // t.addNode(v); t.addEdge(u, v)
+                const int prev = s.last[u];
+                if (lane == 0) {
+                    s.pos[pos_index(n, u, v)] = kNone;
+                    s.fu[depth] = (uint8_t)u; s.fv[depth] = (uint8_t)v;
+                    s.tn[k] = (uint8_t)v; s.par[v] = (uint8_t)u; s.prev[k] = (uint8_t)prev; s.last[u] = (uint8_t)k;
+                }
+                tcount = k + 1;
+                { const unsigned bit = 1u << (v & 31); const int g = v >> 5; t0 |= g == 0 ? bit : 0u; t1 |= g == 1 ? bit : 0u; t2 |= g == 2 ? bit : 0u; t3 |= g == 3 ? bit : 0u; }
+                num_checks++;
+                bool ok;
+                {   // t.checkConstraint(u), PHYTree.java:156-174: running sum of u's children, lanes own samples
+                    double x0, x1, a0, a1, p0 = 0.0, p1 = 0.0;
+                    load_row<SPL>(vaf_s, v, SP, lane, x0, x1);
+                    load_row<SPL>(vaf_s, u, SP, lane, a0, a1);
+                    if (prev != kNoChild) load_row<SPL>(s.psum, prev, SP, lane, p0, p1);
+                    const double s0 = __dadd_rn(p0, x0), s1 = __dadd_rn(p1, x1);
+                    if (SPL == 2) reinterpret_cast<double2 *>(s.psum)[k * 32 + lane] = make_double2(s0, s1);
+                    else s.psum[k * SP + lane] = s0;
+                    bool bad = valid0 && s0 > __dadd_rn(a0, margin);
+                    if (SPL == 2) bad |= valid1 && s1 > __dadd_rn(a1, margin);
+                    ok = !__any_sync(kFull, bad);
+                }
+                if (!ok) { phase = P_AFTER; continue; }
+                __syncwarp();
+                {   // edgesAdded: (v, w) for w in edges.get(v), w not in t, :461-470
+                    const int len = s.adjlen[v];
+                    for (int base = 0; base < len; base += 32) {
+                        const int i = base + lane;
+                        const unsigned w = i < len ? s.adj[v * n + i] : 0u;
+                        push_lanes(i < len && !in_t((int)w), ((unsigned)v << 7) | w);
+                    }
+                }
+                {   // edgesRemoved: every (w, v) in f, in f order, :473-480 (every edge of f leaves a tree node)
+                    unsigned p[4], has[4], rank[4] = {0, 0, 0, 0};
+                    int cnt = 0;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const int w = g * 32 + lane;
+                        const bool cand = g * 32 < n && ((s.inmask[v * 4 + g] & tword(g)) >> lane) & 1u;
+                        p[g] = cand ? s.pos[pos_index(n, w, v)] : kNone;
+                        has[g] = __ballot_sync(kFull, p[g] != kNone);
+                        cnt += __popc(has[g]);
+                    }
+                    const int base = rem_top;
+                    if (cnt > 0) {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            unsigned m = has[g];
+                            while (m) {
+                                const int j = __ffs(m) - 1;
+                                m &= m - 1;
+                                const unsigned pj = __shfl_sync(kFull, p[g], j);
+#pragma unroll
+                                for (int g2 = 0; g2 < 4; g2++) rank[g2] += pj < p[g2];
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            if (p[g] != kNone) {
+                                const int w = g * 32 + lane;
+                                s.rem[base + rank[g]] = (uint16_t)((w << 7) | v);
+                                s.fs[p[g]] = kNone;
+                                s.pos[pos_index(n, w, v)] = kNone;
+                            }
+                        }
+                        f_live -= cnt;
+                        rem_top = base + cnt;
+                    }
+                    if (lane == 0) { s.rembase[depth] = (uint16_t)base; s.remcnt[depth] = (uint16_t)cnt; }
+                }
+                if (num_grow >= max_grow) { status = S_GROW_CAP; break; }   // :490
+                depth++;                                 // grow(t), :495
+                phase = P_ENTER;
+                continue;
+            }
+            if (phase == P_AFTER_RETURN) {               // :497-505
+                if (num_trees == max_trees) { status = S_TREE_CAP; break; }
+                const int v = s.fv[depth];
+                {   // f.removeAll(edgesAdded): the edges of f that leave v
+                    const int len = s.adjlen[v];
+                    int killed = 0;
+                    for (int base = 0; base < len; base += 32) {
+                        const int i = base + lane;
+                        unsigned pp = kNone;
+                        int w = 0;
+                        if (i < len) { w = s.adj[v * n + i]; pp = s.pos[pos_index(n, v, w)]; }
+                        if (pp != kNone) { s.fs[pp] = kNone; s.pos[pos_index(n, v, w)] = kNone; }
+                        killed += __popc(__ballot_sync(kFull, pp != kNone));
+                    }
+                    f_live -= killed;
+                }
+                {   // f.addAll(edgesRemoved)
+                    const int base = s.rembase[depth], cnt = s.remcnt[depth];
+                    for (int j0 = 0; j0 < cnt; j0 += 32) {
+                        const int j = j0 + lane;
+                        push_lanes(j < cnt, j < cnt ? s.rem[base + j] : 0u);
+                    }
+                    rem_top = base;
+                }
+                phase = P_AFTER;
+                __syncwarp();
+            }
+            if (phase == P_AFTER) {                      // :508-530
+                const int u = s.fu[depth], v = s.fv[depth];
+                const int k = tcount - 1;                // t.removeEdge(u, v): v is the newest node
+                const int pv = s.prev[k];
+                tcount = k;
+                { const unsigned bit = ~(1u << (v & 31)); const int g = v >> 5; t0 &= g == 0 ? bit : ~0u; t1 &= g == 1 ? bit : ~0u; t2 &= g == 2 ? bit : ~0u; t3 &= g == 3 ? bit : ~0u; }
+                const int len = s.adjlen[u];             // this.removeEdge(u, v): shift the tail of the list left
+                const int dv = (int)s.indeg[v] - 1;
+                int found = -1;
+                for (int base = 0; base < len; base += 32) {
+                    const int i = base + lane;
+                    const unsigned a = i < len ? s.adj[u * n + i] : 0xffu;
+                    const unsigned m = __ballot_sync(kFull, i < len && a == (unsigned)v);
+                    if (found < 0 && m) found = base + __ffs(m) - 1;
+                    __syncwarp();
+                    if (found >= 0 && i < len && i > found) s.adj[u * n + i - 1] = (uint8_t)a;
+                }
+                if (lane == 0) {
+                    s.last[u] = (uint8_t)pv;
+                    s.adjlen[u] = (uint8_t)(len - 1);
+                    s.indeg[v] = (uint8_t)dv;
+                    s.ff[ff_top] = (uint16_t)((u << 7) | v);         // ff.add(e)
+                }
+                ff_top++;
+                phase = dv == 0 ? P_FINISH : P_LOOP;     // bridge test (lichee_replay.cuh, header comment)
+                if (phase == P_LOOP) continue;
+                __syncwarp();
+            }
+            if (phase == P_FINISH) {                     // :534-540: re-push ff in reverse, re-append to the lists
+                const int base = s.ffbase[depth], cnt = ff_top - base;
+                for (int j0 = 0; j0 < cnt; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool take = j < cnt;
+                    const unsigned code = take ? s.ff[ff_top - 1 - j] : 0u;
+                    push_lanes(take, code);
+                    const int u = code >> 7, v = code & 127;
+                    // several of the edges may leave the same u / enter the same v: group them, keep lane order
+                    const unsigned gu = __match_any_sync(kFull, take ? u : 256 + lane);
+                    const unsigned gv = __match_any_sync(kFull, take ? v : 256 + lane);
+                    const int al = take ? s.adjlen[u] : 0, di = take ? s.indeg[v] : 0;
+                    __syncwarp();
+                    if (take) {
+                        s.adj[u * n + al + __popc(gu & lt)] = (uint8_t)v;
+                        if ((gu >> lane) == 1u) s.adjlen[u] = (uint8_t)(al + __popc(gu));     // highest lane of the group
+                        if ((gv >> lane) == 1u) s.indeg[v] = (uint8_t)(di + __popc(gv));
+                    }
+                    __syncwarp();
+                }
+                ff_top = base;
+                if (depth == 0) { status = S_DONE; break; }
+                depth--;
+                phase = P_AFTER_RETURN;
+            }
         }
+        __syncwarp();
         if (lane == 0) {
-            out->num_grow = h->num_grow; out->num_checks = h->num_checks; out->num_trees = h->num_trees;
-            out->steps = steps; out->status = h->status; out->rec_count = rec_count;
+            Header *h = s.h;
+            h->num_grow = num_grow; h->num_checks = num_checks; h->num_trees = num_trees; h->compactions = compactions;
+            h->top = top; h->f_live = f_live; h->ff_top = ff_top; h->rem_top = rem_top;
+            h->depth = depth; h->tcount = tcount; h->phase = phase; h->status = status;
+            h->inT[0] = t0; h->inT[1] = t1; h->inT[2] = t2; h->inT[3] = t3;
+            out->num_grow = num_grow; out->num_checks = num_checks; out->num_trees = num_trees;
+            out->steps = num_grow - grow_start; out->status = status; out->rec_count = rec_count;
         }
     }
     __syncthreads();
@@ -2272,6 +2480,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         if (keep) {                       // statistics accumulate over the slices of one search
             st.num_trees += before.num_trees; st.num_grow_calls += before.num_grow_calls - 1;
             st.num_checks += before.num_checks; st.num_scored += before.num_scored;
+            st.num_evaluated += before.num_evaluated; st.num_bounded_items += before.num_bounded_items; st.num_leaf_items += before.num_leaf_items;
             st.num_launches += before.num_launches; st.frontier_bytes += before.frontier_bytes;
             st.kernel_ms_total += before.kernel_ms_total; st.status |= before.status;
             for (int i = 0; i < LICHEE_NUM_KERNELS; i++) {
@@ -2412,6 +2621,8 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // no item of this fill can reach the ranked list: its trees are counted, nothing is launched
             fill_items = 0;
             st.num_checks += B * kcand;
+            st.num_bounded_items += B;
+            st.num_leaf_items += B;
             st.num_grow_calls += fill_trees;
             const long long before = seq_base;
             seq_base += fill_trees;
@@ -2513,6 +2724,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // algorithmic bytes of the launch: the count word of every item, the item itself where it was
             // evaluated, the candidate records written
             st.kernel_bytes[LICHEE_K_LEAF] += B * 4ll + (B - (long long)h->h_meta->n_bounded) * (long long)h->stride + m * (long long)sizeof(Cand);
+            st.num_evaluated += (long long)h->h_meta->n_eval;
+            st.num_bounded_items += (long long)h->h_meta->n_bounded;
+            st.num_leaf_items += B;
             if (m > 0) {
                 if (launch_scan(h, lcnt, B, ~0ull >> 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
@@ -2682,6 +2896,7 @@ int run_reference_order(lichee_search *h, bool &completed) {
     st.num_grow_calls = num_grow;
     st.num_checks = num_checks;
     st.num_scored = num_trees;
+    st.num_evaluated = num_trees;
     if (status == replay::S_RUNNING) return LICHEE_OK;          // budget used up: not the reference's answer yet
     completed = true;
     if (status == replay::S_TREE_CAP) st.status |= LICHEE_STATUS_TREE_CAP;
