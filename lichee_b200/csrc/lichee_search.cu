@@ -1797,34 +1797,126 @@ __global__ void export_records(const TopMeta *meta, const Cand *top, const unsig
 //                 samples 0..S-1, children added in insertion order, err += (sum - VAF)^2 one term after
 //                 the other, then Math.sqrt.  No FMA contraction (explicit _rn intrinsics).
 // ------------------------------------------------------------------------------------------
+// PHYTree.computeErrorScore (PHYTree.java:214-233) of one recorded tree, by one warp, in the reference's
+// accumulation order: parents in descending node id (desc: rows in that order), per parent the samples 0..S-1,
+// children added in insertion (treeNodes) order, err += (sum - VAF)^2 one term after the other, Math.sqrt.
+// wA / wB: this lane's word of the record's A (treeNodes) and B (parents) byte strings.  Explicit _rn
+// intrinsics: no FMA contraction.
+template <int SPL>
+__device__ __forceinline__ double score_record(unsigned wA, unsigned wB, const double *vaf_s, const uint8_t *desc, int n, int S,
+                                               int SP, int L, int W, int lane) {
+    const int rmax = (L - 1) / W;
+    const bool valid0 = lane < S, valid1 = SPL == 2 && lane + 32 < S;
+    unsigned pm[4];
+    parent_presence(wB, rmax, pm);
+    double err = 0.0;
+    for (int kk = 0; kk < n; kk++) {
+        const unsigned p = desc[kk];
+        if (!((pm[p >> 5] >> (p & 31)) & 1u)) continue;
+        const unsigned m = __vcmpeq4(wB, p * 0x01010101u);
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r <= rmax; r++) {
+            unsigned kids = __ballot_sync(kFull, (m >> (8 * r)) & 1u);
+            while (kids) {                               // children in insertion (treeNodes) order
+                const int j = __ffs(kids) - 1;
+                kids &= kids - 1;
+                const unsigned c = (__shfl_sync(kFull, wA, j) >> (8 * r)) & 0xffu;
+                double x0, x1;
+                load_row<SPL>(vaf_s, (int)c, SP, lane, x0, x1);
+                s0 = __dadd_rn(s0, x0);
+                if (SPL == 2) s1 = __dadd_rn(s1, x1);
+            }
+        }
+        double a0, a1;
+        load_row<SPL>(vaf_s, (int)p, SP, lane, a0, a1);
+        double t0 = 0.0, t1 = 0.0;
+        if (valid0 && s0 > a0) { const double dd = __dsub_rn(s0, a0); t0 = __dmul_rn(dd, dd); }
+        if (SPL == 2 && valid1 && s1 > a1) { const double dd = __dsub_rn(s1, a1); t1 = __dmul_rn(dd, dd); }
+        unsigned pos = __ballot_sync(kFull, t0 > 0.0);
+        while (pos) {                                    // samples 0..31, one after the other
+            const int j = __ffs(pos) - 1;
+            pos &= pos - 1;
+            err = __dadd_rn(err, __shfl_sync(kFull, t0, j));
+        }
+        if (SPL == 2) {
+            pos = __ballot_sync(kFull, t1 > 0.0);
+            while (pos) {                                // samples 32..63
+                const int j = __ffs(pos) - 1;
+                pos &= pos - 1;
+                err = __dadd_rn(err, __shfl_sync(kFull, t1, j));
+            }
+        }
+    }
+    return __dsqrt_rn(err);
+}
+
 struct ReplayOut {
     long long num_grow, num_checks, num_trees, steps;
     int status, rec_count;
+    int fused;                  // 1: the kernel also scored and ranked the trees; the ranked list is in the result block
+    int count;                  // fused: trees in the ranked list
 };
 
 constexpr int kReplayThreads = 128;
-constexpr int kReplaySmemMax = 225 * 1024;  // dynamic shared memory the replay may take (227 KB per block on sm_100a)
+constexpr int kReplaySmemMax = 208 * 1024;  // dynamic shared memory the replay may take (227 KB per block on sm_100a, 17 KB of it static)
 constexpr int kReplayRecCap = 1 << 15;       // trees one replay launch may record before the batch is scored and merged
+constexpr size_t kPinnedBlob = 256 * 1024;   // pinned: initial replay state (largest layout: 128 nodes, 64 samples, 16256 edges)
+constexpr size_t kPinnedResult = (size_t)LICHEE_MAX_SAVE * (32 + 2 * 128);   // pinned: Cand | tree bytes of a fused result
+constexpr int kFuseMax = 1024;               // a search with at most this many trees is scored and ranked by the replay launch itself
 
-template <int SPL>
+struct FuseKey { double score; unsigned idx, pad; };
+
+struct ReplayArgs {             // (one struct: the argument list had outgrown a readable signature)
+    replay::Layout lay;
+    const unsigned char *blob_src;   // state to resume from: the pinned initial state (first launch) or blob_dst
+    unsigned char *blob_dst;         // device copy the state is saved to when the launch pauses
+    int blob_in_smem;
+    const double *vaf;               // centroid matrix, row space
+    int S, L, stride;
+    double margin;
+    unsigned char *records;          // record buffer of this launch
+    long long record_bytes;
+    int rec_cap;
+    long long step_quota, grow_limit;
+    ReplayOut *out;                  // pinned, device-visible
+    // first launch only: initialise the ranked list; fuse: score + rank here when the whole search fits
+    int first, fuse, num_save;
+    TopMeta *meta;
+    const uint8_t *desc_rows;
+    unsigned char *result;           // pinned, device-visible: Cand[num_save] | tree bytes (2 x stride each)
+};
+
+template <int SPL, int NG>
 __global__ void __launch_bounds__(kReplayThreads, 1)
-replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const double *__restrict__ vaf_g, int S,
-              double margin, unsigned char *records, long long record_bytes, int rec_cap, int L, int stride,
-              long long step_quota, long long grow_limit, ReplayOut *out) {
+replay_kernel(const __grid_constant__ ReplayArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int fuse_count_s;
+    const replay::Layout &lay = a.lay;
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
-    const int SP = lay.SP;
+    const int SP = lay.SP, S = a.S, L = a.L, stride = a.stride;
+    const double margin = a.margin;
+    unsigned char *records = a.records;
+    const long long record_bytes = a.record_bytes;
+    const int rec_cap = a.rec_cap;
+    ReplayOut *out = a.out;
     const unsigned vaf_bytes = (unsigned)lay.n * SP * 8u;
-    unsigned char *blob = blob_in_smem ? smem_raw + vaf_bytes : blob_g;
+    // the state is worked on in shared memory when it fits, else in place in the device copy
+    unsigned char *blob = a.blob_in_smem ? smem_raw + vaf_bytes : a.blob_dst;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(vaf_g);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.vaf);
         uint4 *dst = reinterpret_cast<uint4 *>(vaf_s);
         for (unsigned i = threadIdx.x; i < vaf_bytes / 16; i += blockDim.x) dst[i] = src[i];
-        if (blob_in_smem) {
-            const uint4 *bs = reinterpret_cast<const uint4 *>(blob_g);
+        if (a.blob_in_smem || a.blob_src != a.blob_dst) {
+            const uint4 *bs = reinterpret_cast<const uint4 *>(a.blob_src);
             uint4 *bd = reinterpret_cast<uint4 *>(blob);
             for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
         }
+        if (a.first && threadIdx.x == 0) {
+            TopMeta *meta = a.meta;
+            meta->count = 0; meta->pad = 0; meta->tau = INFINITY; meta->n_cand = 0; meta->n_valid = 0;
+            meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
+        }
+        if (threadIdx.x == 0) fuse_count_s = -1;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -1846,9 +1938,11 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
         int depth = s.h->depth, tcount = s.h->tcount, phase = s.h->phase, status = s.h->status;
         unsigned t0 = s.h->inT[0], t1 = s.h->inT[1], t2 = s.h->inT[2], t3 = s.h->inT[3];
         const long long grow_start = num_grow;
+        const long long step_quota = a.step_quota, grow_limit = a.grow_limit;
         int rec_count = 0;
-        auto tword = [&](int g) { return g == 0 ? t0 : g == 1 ? t1 : g == 2 ? t2 : t3; };
-        auto in_t = [&](int v) { return (tword(v >> 5) >> (v & 31)) & 1u; };
+        // NG = 1: at most 32 nodes (every real data set), one membership word and one pass per list scan
+        auto tword = [&](int g) { return NG == 1 ? t0 : g == 0 ? t0 : g == 1 ? t1 : g == 2 ? t2 : t3; };
+        auto in_t = [&](int v) { return NG == 1 ? (t0 >> v) & 1u : (tword(v >> 5) >> (v & 31)) & 1u; };
         auto compact = [&]() {                           // squeeze the tombstones out of fs
             __syncwarp();
             int k = 0;
@@ -1937,7 +2031,8 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
                     s.tn[k] = (uint8_t)v; s.par[v] = (uint8_t)u; s.prev[k] = (uint8_t)prev; s.last[u] = (uint8_t)k;
                 }
                 tcount = k + 1;
-                { const unsigned bit = 1u << (v & 31); const int g = v >> 5; t0 |= g == 0 ? bit : 0u; t1 |= g == 1 ? bit : 0u; t2 |= g == 2 ? bit : 0u; t3 |= g == 3 ? bit : 0u; }
+                if (NG == 1) t0 |= 1u << v;
+                else { const unsigned bit = 1u << (v & 31); const int g = v >> 5; t0 |= g == 0 ? bit : 0u; t1 |= g == 1 ? bit : 0u; t2 |= g == 2 ? bit : 0u; t3 |= g == 3 ? bit : 0u; }
                 num_checks++;
                 bool ok;
                 {   // t.checkConstraint(u), PHYTree.java:156-174: running sum of u's children, lanes own samples
@@ -1956,38 +2051,41 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
                 __syncwarp();
                 {   // edgesAdded: (v, w) for w in edges.get(v), w not in t, :461-470
                     const int len = s.adjlen[v];
-                    for (int base = 0; base < len; base += 32) {
+                    for (int base = 0; base < (NG == 1 ? 1 : len); base += 32) {
                         const int i = base + lane;
                         const unsigned w = i < len ? s.adj[v * n + i] : 0u;
                         push_lanes(i < len && !in_t((int)w), ((unsigned)v << 7) | w);
                     }
                 }
                 {   // edgesRemoved: every (w, v) in f, in f order, :473-480 (every edge of f leaves a tree node)
-                    unsigned p[4], has[4], rank[4] = {0, 0, 0, 0};
+                    unsigned p[NG], has[NG], rank[NG];
                     int cnt = 0;
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
+                    for (int g = 0; g < NG; g++) {
                         const int w = g * 32 + lane;
                         const bool cand = g * 32 < n && ((s.inmask[v * 4 + g] & tword(g)) >> lane) & 1u;
                         p[g] = cand ? s.pos[pos_index(n, w, v)] : kNone;
                         has[g] = __ballot_sync(kFull, p[g] != kNone);
                         cnt += __popc(has[g]);
+                        rank[g] = 0;
                     }
                     const int base = rem_top;
                     if (cnt > 0) {
+                        if (cnt > 1) {
 #pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            unsigned m = has[g];
-                            while (m) {
-                                const int j = __ffs(m) - 1;
-                                m &= m - 1;
-                                const unsigned pj = __shfl_sync(kFull, p[g], j);
+                            for (int g = 0; g < NG; g++) {
+                                unsigned m = has[g];
+                                while (m) {
+                                    const int j = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    const unsigned pj = __shfl_sync(kFull, p[g], j);
 #pragma unroll
-                                for (int g2 = 0; g2 < 4; g2++) rank[g2] += pj < p[g2];
+                                    for (int g2 = 0; g2 < NG; g2++) rank[g2] += pj < p[g2];
+                                }
                             }
                         }
 #pragma unroll
-                        for (int g = 0; g < 4; g++) {
+                        for (int g = 0; g < NG; g++) {
                             if (p[g] != kNone) {
                                 const int w = g * 32 + lane;
                                 s.rem[base + rank[g]] = (uint16_t)((w << 7) | v);
@@ -2011,7 +2109,7 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
                 {   // f.removeAll(edgesAdded): the edges of f that leave v
                     const int len = s.adjlen[v];
                     int killed = 0;
-                    for (int base = 0; base < len; base += 32) {
+                    for (int base = 0; base < (NG == 1 ? 1 : len); base += 32) {
                         const int i = base + lane;
                         unsigned pp = kNone;
                         int w = 0;
@@ -2023,7 +2121,7 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
                 }
                 {   // f.addAll(edgesRemoved)
                     const int base = s.rembase[depth], cnt = s.remcnt[depth];
-                    for (int j0 = 0; j0 < cnt; j0 += 32) {
+                    for (int j0 = 0; j0 < (NG == 1 ? (cnt > 0) : cnt); j0 += 32) {
                         const int j = j0 + lane;
                         push_lanes(j < cnt, j < cnt ? s.rem[base + j] : 0u);
                     }
@@ -2037,11 +2135,12 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
                 const int k = tcount - 1;                // t.removeEdge(u, v): v is the newest node
                 const int pv = s.prev[k];
                 tcount = k;
-                { const unsigned bit = ~(1u << (v & 31)); const int g = v >> 5; t0 &= g == 0 ? bit : ~0u; t1 &= g == 1 ? bit : ~0u; t2 &= g == 2 ? bit : ~0u; t3 &= g == 3 ? bit : ~0u; }
+                if (NG == 1) t0 &= ~(1u << v);
+                else { const unsigned bit = ~(1u << (v & 31)); const int g = v >> 5; t0 &= g == 0 ? bit : ~0u; t1 &= g == 1 ? bit : ~0u; t2 &= g == 2 ? bit : ~0u; t3 &= g == 3 ? bit : ~0u; }
                 const int len = s.adjlen[u];             // this.removeEdge(u, v): shift the tail of the list left
                 const int dv = (int)s.indeg[v] - 1;
                 int found = -1;
-                for (int base = 0; base < len; base += 32) {
+                for (int base = 0; base < (NG == 1 ? 1 : len); base += 32) {
                     const int i = base + lane;
                     const unsigned a = i < len ? s.adj[u * n + i] : 0xffu;
                     const unsigned m = __ballot_sync(kFull, i < len && a == (unsigned)v);
@@ -2095,11 +2194,68 @@ replay_kernel(replay::Layout lay, unsigned char *blob_g, int blob_in_smem, const
             h->inT[0] = t0; h->inT[1] = t1; h->inT[2] = t2; h->inT[3] = t3;
             out->num_grow = num_grow; out->num_checks = num_checks; out->num_trees = num_trees;
             out->steps = num_grow - grow_start; out->status = status; out->rec_count = rec_count;
+            // the whole search is in this launch's record buffer and small: score and rank it right here
+            const bool fuse = a.fuse && status != S_RUNNING && num_trees == (long long)rec_count && rec_count <= kFuseMax;
+            out->fused = fuse ? 1 : 0;
+            out->count = 0;
+            if (fuse) fuse_count_s = rec_count;
         }
     }
     __syncthreads();
-    if (blob_in_smem) {
-        uint4 *bd = reinterpret_cast<uint4 *>(blob_g);
+    const int fuse_count = fuse_count_s;
+    if (fuse_count >= 0) {
+        // Fused finish (a search of a real data set is a handful of trees: three more launches and two more
+        // host round trips would cost several times the search).  Scores: one warp per tree, the reference's
+        // accumulation order (score_record).  Ranking: Collections.sort is stable, so the order is (score,
+        // discovery index); bitonic sort of the keys in shared memory.  The ranked list goes straight to the
+        // pinned result block: Cand[num_save] | tree bytes.
+        __shared__ FuseKey key_s[kFuseMax];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, W = stride >> 2;
+        int N = 1;
+        while (N < fuse_count) N <<= 1;
+        for (int t = wid; t < fuse_count; t += kReplayThreads / 32) {
+            unsigned char *rp = records + (size_t)t * record_bytes;
+            const unsigned wA = lane < W ? reinterpret_cast<const unsigned *>(rp + 24)[lane] : 0xffffffffu;
+            const unsigned wB = lane < W ? reinterpret_cast<const unsigned *>(rp + 24 + stride)[lane] : 0xffffffffu;
+            const double score = score_record<SPL>(wA, wB, vaf_s, a.desc_rows, lay.n, S, SP, L, W, lane);
+            if (lane == 0) { key_s[t].score = score; key_s[t].idx = (unsigned)t; }
+        }
+        for (int t = fuse_count + threadIdx.x; t < N; t += blockDim.x) { key_s[t].score = INFINITY; key_s[t].idx = 0xffffffffu; }
+        __syncthreads();
+        for (int k = 2; k <= N; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < N; t += blockDim.x) {
+                    const int x = t ^ j;
+                    if (x > t) {
+                        const FuseKey ka = key_s[t], kb = key_s[x];
+                        const bool b_less = kb.score < ka.score || (kb.score == ka.score && kb.idx < ka.idx);
+                        if (b_less == ((t & k) == 0)) { key_s[t] = kb; key_s[x] = ka; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const int newc = fuse_count < a.num_save ? fuse_count : a.num_save;
+        Cand *top = reinterpret_cast<Cand *>(a.result);
+        unsigned *tree = reinterpret_cast<unsigned *>(a.result + sizeof(Cand) * (size_t)a.num_save);
+        for (int t = threadIdx.x; t < newc; t += blockDim.x) {
+            Cand c;
+            c.score = key_s[t].score; c.seq = (long long)key_s[t].idx; c.part = 0;
+            c.origin = 0x80000000u | (unsigned)t; c.pstar = 0; c.pad = 0;
+            top[t] = c;
+        }
+        for (int t = wid; t < newc; t += kReplayThreads / 32) {
+            const unsigned *src = reinterpret_cast<const unsigned *>(records + (size_t)key_s[t].idx * record_bytes + 24);
+            for (int j = lane; j < 2 * W; j += 32) tree[(size_t)t * 2 * W + j] = src[j];
+        }
+        if (threadIdx.x == 0) {
+            out->count = newc;
+            a.meta->count = 0;                          // the device-resident list is not used by a fused result
+        }
+        return;                                          // the search is over: no state to save
+    }
+    if (a.blob_in_smem) {
+        uint4 *bd = reinterpret_cast<uint4 *>(a.blob_dst);
         const uint4 *bs = reinterpret_cast<const uint4 *>(blob);
         for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
     }
@@ -2119,55 +2275,13 @@ score_ref_kernel(DevNet net, unsigned char *records, long long record_bytes, int
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int SP = net.SP, W = net.stride >> 2, L = net.L;
-    const int rmax = (L - 1) / W;
-    const bool valid0 = lane < net.S, valid1 = SPL == 2 && lane + 32 < net.S;
     const int warp0 = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), nwarps = gridDim.x * kWarpsPerBlock;
     for (int t = warp0; t < count; t += nwarps) {
         unsigned char *rp = records + (size_t)t * record_bytes;
         const unsigned wA = lane < W ? reinterpret_cast<const unsigned *>(rp + 24)[lane] : 0xffffffffu;
         const unsigned wB = lane < W ? reinterpret_cast<const unsigned *>(rp + 24 + net.stride)[lane] : 0xffffffffu;
-        unsigned pm[4];
-        parent_presence(wB, rmax, pm);
-        double err = 0.0;
-        for (int kk = 0; kk < net.n; kk++) {
-            const unsigned p = desc_s[kk];
-            if (!((pm[p >> 5] >> (p & 31)) & 1u)) continue;
-            const unsigned m = __vcmpeq4(wB, p * 0x01010101u);
-            double s0 = 0.0, s1 = 0.0;
-            for (int r = 0; r <= rmax; r++) {
-                unsigned kids = __ballot_sync(kFull, (m >> (8 * r)) & 1u);
-                while (kids) {                           // children in insertion (treeNodes) order
-                    const int j = __ffs(kids) - 1;
-                    kids &= kids - 1;
-                    const unsigned c = (__shfl_sync(kFull, wA, j) >> (8 * r)) & 0xffu;
-                    double x0, x1;
-                    load_row<SPL>(vaf_s, (int)c, SP, lane, x0, x1);
-                    s0 = __dadd_rn(s0, x0);
-                    if (SPL == 2) s1 = __dadd_rn(s1, x1);
-                }
-            }
-            double a0, a1;
-            load_row<SPL>(vaf_s, (int)p, SP, lane, a0, a1);
-            double t0 = 0.0, t1 = 0.0;
-            if (valid0 && s0 > a0) { const double dd = __dsub_rn(s0, a0); t0 = __dmul_rn(dd, dd); }
-            if (SPL == 2 && valid1 && s1 > a1) { const double dd = __dsub_rn(s1, a1); t1 = __dmul_rn(dd, dd); }
-            unsigned pos = __ballot_sync(kFull, t0 > 0.0);
-            while (pos) {                                // samples 0..31, one after the other
-                const int j = __ffs(pos) - 1;
-                pos &= pos - 1;
-                err = __dadd_rn(err, __shfl_sync(kFull, t0, j));
-            }
-            if (SPL == 2) {
-                pos = __ballot_sync(kFull, t1 > 0.0);
-                while (pos) {                            // samples 32..63
-                    const int j = __ffs(pos) - 1;
-                    pos &= pos - 1;
-                    err = __dadd_rn(err, __shfl_sync(kFull, t1, j));
-                }
-            }
-        }
+        const double score = score_record<SPL>(wA, wB, vaf_s, desc_s, net.n, net.S, SP, L, W, lane);
         if (lane == 0) {
-            const double score = __dsqrt_rn(err);
             *reinterpret_cast<double *>(rp) = score;
             Cand c;
             c.score = score;
@@ -2228,6 +2342,7 @@ struct DevCtx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk[2][6] = {};
     void *pinned = nullptr;
+    void *pinned_big = nullptr;          // initial replay state | fused result block (device-visible)
 };
 struct CtxPool {
     std::mutex mu;
@@ -2294,9 +2409,11 @@ struct lichee_search {
     bool cyclic = false;                     // the network has a directed cycle: only the replay can search it
     bool ref_result = false;                 // the ranked list on the host came from the replay (records of 2 x stride bytes)
     replay::Layout rlay{};
-    std::vector<unsigned char> rblob0;       // initial state of getLineageTrees(), uploaded before every replay
+    unsigned char *h_big = nullptr;          // pinned: [initial state of getLineageTrees() | fused result block]
+    unsigned char *rblob0 = nullptr;         // = h_big: the initial state, read by the first replay launch of every run
+    unsigned char *h_result = nullptr;       // = h_big + kPinnedBlob
     bool rblob_in_smem = false;
-    DevBuf b_rblob, b_rrec, b_rout;          // state blob, record buffer, ReplayOut
+    DevBuf b_rblob, b_rrec;                  // state blob (device copy), record buffer
     ReplayOut *h_rout = nullptr;             // pinned
 
     unsigned *level(int lv) { return static_cast<unsigned *>(b_level[lv].p); }
@@ -2824,30 +2941,42 @@ int run_reference_order(lichee_search *h, bool &completed) {
     lichee_search_stats &st = h->stats;
     st = lichee_search_stats{};
     const long long budget = h->prm.ref_order_budget > 0 ? h->prm.ref_order_budget : LICHEE_DEFAULT_REF_ORDER_BUDGET;
-    const replay::Header *h0 = reinterpret_cast<const replay::Header *>(h->rblob0.data());
+    const replay::Header *h0 = reinterpret_cast<const replay::Header *>(h->rblob0);
     const long long rb = 24 + 2ll * h->stride;
-    init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
     h->flip = 0;
     h->ref_result = true;
     CK(cudaEventRecord(h->ev0, h->stream));
     int status = h0->status;
     long long num_grow = 0, num_checks = 0, num_trees = 0;
-    if (status == replay::S_RUNNING) {
-        CK(cudaMemcpyAsync(h->b_rblob.p, h->rblob0.data(), h->rlay.total, cudaMemcpyHostToDevice, h->stream));
-        ReplayOut *d_out = static_cast<ReplayOut *>(h->b_rout.p);
+    bool fused = false;
+    if (status != replay::S_RUNNING) {                       // the root has no edge: no grow() call at all
+        init_meta<<<1, 1, 0, h->stream>>>(h->d_meta());
+        CK(cudaGetLastError());
+    } else {
+        ReplayArgs a;
+        a.lay = h->rlay;
+        a.blob_src = h->rblob0;                                // pinned initial state, read by the kernel itself
+        a.blob_dst = static_cast<unsigned char *>(h->b_rblob.p);
+        a.blob_in_smem = h->rblob_in_smem ? 1 : 0;
+        a.vaf = h->net.vaf; a.S = h->S; a.L = h->L; a.stride = h->stride; a.margin = h->prm.vaf_error_margin;
+        a.record_bytes = rb;
+        a.step_quota = 1ll << 22; a.grow_limit = budget;
+        a.out = h->h_rout;                                     // pinned: read after the synchronize, no copy
+        a.first = 1; a.fuse = 1; a.num_save = h->prm.num_save;
+        a.meta = h->d_meta(); a.desc_rows = h->net.desc_rows; a.result = h->h_result;
         const size_t smem = (size_t)h->n * h->SP * sizeof(double) + (h->rblob_in_smem ? h->rlay.total : 0);
+        const bool small = h->n <= 32;
         // record buffer: small for the first launch (most real searches end inside it), full size afterwards
         int rec_cap = 4096;
         for (;;) {
             if (ensure(h, h->b_rrec, (size_t)rb * rec_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
             unsigned char *rec = static_cast<unsigned char *>(h->b_rrec.p);
+            a.records = rec; a.rec_cap = rec_cap;
             CK(cudaEventRecord(h->evk[0][0], h->stream));
-            replay_kernel<SPL><<<1, kReplayThreads, smem, h->stream>>>(
-                h->rlay, static_cast<unsigned char *>(h->b_rblob.p), h->rblob_in_smem ? 1 : 0, h->net.vaf, h->S,
-                h->prm.vaf_error_margin, rec, rb, rec_cap, h->L, h->stride, 1ll << 22, budget, d_out);
+            if (small) replay_kernel<SPL, 1><<<1, kReplayThreads, smem, h->stream>>>(a);
+            else replay_kernel<SPL, 4><<<1, kReplayThreads, smem, h->stream>>>(a);
             CK(cudaGetLastError());
             CK(cudaEventRecord(h->evk[0][1], h->stream));
-            CK(cudaMemcpyAsync(h->h_rout, d_out, sizeof(ReplayOut), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             st.num_launches++;
             st.kernel_launches[LICHEE_K_CHECK]++;
@@ -2858,6 +2987,8 @@ int run_reference_order(lichee_search *h, bool &completed) {
             num_grow = h->h_rout->num_grow; num_checks = h->h_rout->num_checks; num_trees = h->h_rout->num_trees;
             const int m = h->h_rout->rec_count;
             st.kernel_bytes[LICHEE_K_CHECK] += (long long)m * rb;
+            if (h->h_rout->fused) { fused = true; break; }
+            a.first = 0; a.fuse = 0; a.blob_src = a.blob_dst;
             if (m > 0) {
                 // score the batch (one warp per tree) and merge it into the ranked list
                 if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)std::max(m, kSelTile)) != LICHEE_OK) return LICHEE_ERR_CUDA;
@@ -2901,6 +3032,16 @@ int run_reference_order(lichee_search *h, bool &completed) {
     completed = true;
     if (status == replay::S_TREE_CAP) st.status |= LICHEE_STATUS_TREE_CAP;
     if (status == replay::S_GROW_CAP) st.status |= LICHEE_STATUS_GROW_CAP;
+    if (fused) {
+        // the ranked list is already in pinned host memory
+        const unsigned count = (unsigned)h->h_rout->count;
+        const Cand *top = reinterpret_cast<const Cand *>(h->h_result);
+        const unsigned char *tree = h->h_result + sizeof(Cand) * (size_t)h->prm.num_save;
+        h->h_top.assign(top, top + count);
+        h->h_tree.assign(tree, tree + (size_t)count * 2 * h->stride);
+        st.num_saved = count;
+        return LICHEE_OK;
+    }
     return fetch_top(h);
 }
 
@@ -2963,6 +3104,7 @@ int lichee_release_cached_memory(void) {
         DevCtx &c = kv.second;
         cudaSetDevice(kv.first);
         if (c.pinned) cudaFreeHost(c.pinned);
+        if (c.pinned_big) cudaFreeHost(c.pinned_big);
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) if (c.evk[a][b]) cudaEventDestroy(c.evk[a][b]);
@@ -2996,13 +3138,24 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_sched);
     give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag);
     give_back(h, h->b_lmask); give_back(h, h->b_lcnt);
-    give_back(h, h->b_rblob); give_back(h, h->b_rrec); give_back(h, h->b_rout);
+    give_back(h, h->b_rblob); give_back(h, h->b_rrec);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
-    if (h->stream) {
+    {
         DevCtx c;
-        c.stream = h->stream; c.ev0 = h->ev0; c.ev1 = h->ev1; c.pinned = h->h_scan;
-        for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) c.evk[x][y] = h->evk[x][y];
-        g_ctx.put(h->device, c);
+        c.stream = h->stream; c.ev0 = h->ev0; c.ev1 = h->ev1; c.pinned = h->h_scan; c.pinned_big = h->h_big;
+        bool whole = c.stream && c.ev0 && c.ev1 && c.pinned && c.pinned_big;
+        for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) { c.evk[x][y] = h->evk[x][y]; whole = whole && c.evk[x][y]; }
+        if (whole) {
+            g_ctx.put(h->device, c);
+        } else {
+            // a create that failed half way: nothing of it goes back to the pool
+            if (c.pinned) cudaFreeHost(c.pinned);
+            if (c.pinned_big) cudaFreeHost(c.pinned_big);
+            if (c.ev0) cudaEventDestroy(c.ev0);
+            if (c.ev1) cudaEventDestroy(c.ev1);
+            for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) if (c.evk[x][y]) cudaEventDestroy(c.evk[x][y]);
+            if (c.stream) cudaStreamDestroy(c.stream);
+        }
     }
     delete h;
     return LICHEE_OK;
@@ -3097,12 +3250,14 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         DevCtx c;
         if (g_ctx.get(h->device, c)) {
             h->stream = c.stream; h->ev0 = c.ev0; h->ev1 = c.ev1; h->h_scan = static_cast<ScanOut *>(c.pinned);
+            h->h_big = static_cast<unsigned char *>(c.pinned_big);
             for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) h->evk[x][y] = c.evk[x][y];
         } else {
             CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
             for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
             CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta) + sizeof(Sched) + sizeof(ReplayOut)));
+            CKD(cudaMallocHost(&h->h_big, kPinnedBlob + kPinnedResult));
         }
     }
     const int Lp = std::max(1, h->L);
@@ -3235,7 +3390,9 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     }
     h->smem = (size_t)n * h->SP * sizeof(double) + kMaxN;
     h->smem_leaf = h->smem;
-    if (h->device >= 0 && h->device < 64 && !g_ctx.attrs_set[h->device]) {
+    if (h->device >= 0 && h->device < 64) {
+      std::lock_guard<std::mutex> g(g_ctx.mu);
+      if (!g_ctx.attrs_set[h->device]) {
         // opt in to the largest dynamic shared memory any network needs (128 rows x 64 samples)
         const int mx = kMaxN * 64 * (int)sizeof(double) + kMaxN;
         CKD(cudaFuncSetAttribute(check_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -3249,6 +3406,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         CKD(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 3 * kSelTile)));
         CKD(cudaFuncSetAttribute(select_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Cand) * 2 * kSelTile)));
         g_ctx.attrs_set[h->device] = true;
+      }
     }
     {
         // reference-order replay: adjacency lists in ROW space, list order kept
@@ -3260,17 +3418,20 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
             roff[q + 1] = (int)ridx.size();
         }
         h->rlay = replay::make_layout(n, h->SP, (int)ridx.size());
-        h->rblob0.assign(h->rlay.total, 0);
-        replay::init_blob(h->rblob0.data(), h->rlay, roff.data(), ridx.data(), params->max_num_grow_calls, params->max_num_trees);
+        if (h->rlay.total > kPinnedBlob) { set_err("replay state of %u bytes exceeds the pinned block", h->rlay.total); lichee_search_destroy(h); return LICHEE_ERR_STATE; }
+        h->rblob0 = h->h_big;
+        h->h_result = h->h_big + kPinnedBlob;
+        replay::init_blob(h->rblob0, h->rlay, roff.data(), ridx.data(), params->max_num_grow_calls, params->max_num_trees);
         h->rblob_in_smem = (size_t)n * h->SP * sizeof(double) + h->rlay.total <= (size_t)kReplaySmemMax;
         CKE(ensure(h, h->b_rblob, h->rlay.total));
-        CKE(ensure(h, h->b_rout, 256));
     }
     if (h->device >= 0 && h->device < 64) {
         std::lock_guard<std::mutex> g(g_ctx.mu);
         if (!g_ctx.attrs2_set[h->device]) {
-            CKD(cudaFuncSetAttribute(replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
-            CKD(cudaFuncSetAttribute(replay_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
             const int mx = kMaxN * 64 * (int)sizeof(double) + kMaxN;
             CKD(cudaFuncSetAttribute(score_ref_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
             CKD(cudaFuncSetAttribute(score_ref_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -3416,9 +3577,10 @@ int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_pt
                                                           h->stride >> 2, h->prm.num_save, d, rb);
     CK(cudaGetLastError());
     if (!device_ptr) {
-        CK(cudaMemcpyAsync(dst, d, (size_t)rb * h->prm.num_save, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        cudaError_t e1 = cudaMemcpyAsync(dst, d, (size_t)rb * h->prm.num_save, cudaMemcpyDeviceToHost, h->stream);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(h->stream);
         cudaFree(d);
+        CK(e1);
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }
@@ -3442,7 +3604,7 @@ int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_
     }
     records_to_cands<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(d, rb, n, h->d_cands(0), h->d_meta());
     CK(cudaGetLastError());
-    if (run_select(h, h->d_cands(0), n, nullptr, 1, d, rb) != LICHEE_OK) return LICHEE_ERR_CUDA;
+    if (run_select(h, h->d_cands(0), n, nullptr, 1, d, rb) != LICHEE_OK) { if (tmp) cudaFree(tmp); return LICHEE_ERR_CUDA; }
     const int rc = fetch_top(h);
     if (tmp) cudaFree(tmp);
     return rc;

@@ -10,11 +10,11 @@ import lichee_b200
 from lichee_b200.synth import make_instance
 
 
-def phases(adj, vaf, margin, save, max_trees=100000, reps=20):
+def phases(adj, vaf, margin, save, max_trees=100000, reps=20, budget=0):
     rows = []
     for _ in range(reps):
         t = [time.perf_counter()]
-        s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=save, max_num_trees=max_trees); t.append(time.perf_counter())
+        s = lichee_b200.LineageSearch(adj, vaf, margin, num_save=save, max_num_trees=max_trees, ref_order_budget=budget); t.append(time.perf_counter())
         st = s.run(); t.append(time.perf_counter())
         tr = s.trees(); t.append(time.perf_counter())
         s.close(); t.append(time.perf_counter())
@@ -30,12 +30,14 @@ if __name__ == "__main__":
     net, prm = make_instance(120, 64, seed=2026)
     v = np.ascontiguousarray(net.aaf, dtype=np.float64)
     if os.environ.get("LICHEE_DEBUG"):
-        phases(net.adj, v, prm.vaf_error_margin, 1000, reps=1)
+        phases(net.adj, v, prm.vaf_error_margin, 1000, reps=1, budget=-1)
         sys.exit(0)
-    print("120x64 default caps -s 1000:", phases(net.adj, v, prm.vaf_error_margin, 1000))
+    print("120x64 default caps -s 1000 (canonical):", phases(net.adj, v, prm.vaf_error_margin, 1000, budget=-1))
     net, prm = make_instance(40, 20, seed=2026)
     v = np.ascontiguousarray(net.aaf, dtype=np.float64)
-    print("40x20 default caps -s 100:", phases(net.adj, v, prm.vaf_error_margin, 100))
+    print("40x20 default caps -s 100 (canonical):", phases(net.adj, v, prm.vaf_error_margin, 100, budget=-1))
     for e in json.load(open(os.path.join(ROOT, "tests", "golden", "networks_bundled.json"))):
         if e["clustering"] == "single" and not e["complete_edges"] and e["dataset"] in ("ccRCC/RK26.txt", "hgsc/case5.txt"):
-            print(e["dataset"], phases(e["adj"], np.array(e["aaf"]), e["vaf_error_margin"], 100 if "hgsc" in e["dataset"] else 1))
+            for budget in (0, -1):
+                print(e["dataset"], "reference order" if budget == 0 else "canonical",
+                      phases(e["adj"], np.array(e["aaf"]), e["vaf_error_margin"], 100 if "hgsc" in e["dataset"] else 1, budget=budget))
