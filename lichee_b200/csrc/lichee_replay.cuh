@@ -90,13 +90,14 @@ inline Layout make_layout(int n, int SP, int E) {
     memset(&L, 0, sizeof(L));
     L.n = n; L.SP = SP; L.E = E;
     L.fs_cap = 2 * E + 2 * n + 64;
+    if (L.fs_cap < 256) L.fs_cap = 256;
     unsigned o = rp_align((unsigned)sizeof(Header), 16);
     L.o_psum = o;    o = rp_align(o + (unsigned)n * SP * 8u, 16);
-    L.o_adj = o;     o = rp_align(o + (unsigned)n * n, 16);
+    L.o_adj = o;     o = rp_align(o + (unsigned)n * n + 32u, 16);      // (+32: a warp may load 32 entries from the start of any row)
     L.o_adjlen = o;  o = rp_align(o + (unsigned)n, 16);
     L.o_indeg = o;   o = rp_align(o + (unsigned)n, 16);
     L.o_inmask = o;  o = rp_align(o + (unsigned)n * 16u, 16);
-    L.o_pos = o;     o = rp_align(o + (unsigned)n * n * 2u, 16);
+    L.o_pos = o;     o = rp_align(o + ((unsigned)n * n + 32u) * 2u, 16);
     L.o_fs = o;      o = rp_align(o + (unsigned)L.fs_cap * 2u, 16);
     L.o_ff = o;      o = rp_align(o + (unsigned)(E + 1) * 2u, 16);
     L.o_rem = o;     o = rp_align(o + (unsigned)(E + 1) * 2u, 16);

@@ -1886,7 +1886,11 @@ struct ReplayArgs {             // (one struct: the argument list had outgrown a
     unsigned char *result;           // pinned, device-visible: Cand[num_save] | tree bytes (2 x stride each)
 };
 
-template <int SPL, int NG>
+// SPL: samples per lane (1: <= 32 samples, 2: <= 64).  NG: 32-node groups (1: <= 32 nodes, the latency-oriented loop; 4).
+// BS: the state blob is worked on in shared memory -- a template parameter so that every access to it compiles to
+// LDS/STS with 32-bit addresses; with a run-time choice between shared and global memory all of them were generic
+// loads with 64-bit address arithmetic (a third more instructions, measured).
+template <int SPL, int NG, bool BS>
 __global__ void __launch_bounds__(kReplayThreads, 1)
 replay_kernel(const __grid_constant__ ReplayArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1901,12 +1905,12 @@ replay_kernel(const __grid_constant__ ReplayArgs a) {
     ReplayOut *out = a.out;
     const unsigned vaf_bytes = (unsigned)lay.n * SP * 8u;
     // the state is worked on in shared memory when it fits, else in place in the device copy
-    unsigned char *blob = a.blob_in_smem ? smem_raw + vaf_bytes : a.blob_dst;
+    unsigned char *blob = BS ? smem_raw + vaf_bytes : a.blob_dst;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.vaf);
         uint4 *dst = reinterpret_cast<uint4 *>(vaf_s);
         for (unsigned i = threadIdx.x; i < vaf_bytes / 16; i += blockDim.x) dst[i] = src[i];
-        if (a.blob_in_smem || a.blob_src != a.blob_dst) {
+        if (BS || a.blob_src != a.blob_dst) {
             const uint4 *bs = reinterpret_cast<const uint4 *>(a.blob_src);
             uint4 *bd = reinterpret_cast<uint4 *>(blob);
             for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
@@ -1974,34 +1978,38 @@ replay_kernel(const __grid_constant__ ReplayArgs a) {
             top += c;
             f_live += c;
         };
+        const long long stop_at = grow_limit < grow_start + step_quota ? grow_limit : grow_start + step_quota;
+        auto record_tree = [&]() {                       // spanningTrees.add(L.clone()): one record, words split over the lanes
+            unsigned char *rp = records + (size_t)rec_count * record_bytes;
+            if (lane == 0) {
+                *reinterpret_cast<double *>(rp) = 0.0;
+                *reinterpret_cast<long long *>(rp + 8) = num_trees;
+                *reinterpret_cast<int *>(rp + 16) = 0;
+                *reinterpret_cast<int *>(rp + 20) = 1;
+            }
+            if (lane < W) {
+                unsigned wa = 0, wb = 0;
+                for (int q = 3; q >= 0; q--) {
+                    const int i = q * W + lane;          // tree position i <-> treeNodes[i + 1]
+                    unsigned ab = 0xffu, bb = 0xffu;
+                    if (i < L) { ab = s.tn[i + 1]; bb = s.par[ab]; }
+                    wa = (wa << 8) | ab;
+                    wb = (wb << 8) | bb;
+                }
+                reinterpret_cast<unsigned *>(rp + 24)[lane] = wa;
+                reinterpret_cast<unsigned *>(rp + 24 + stride)[lane] = wb;
+            }
+            rec_count++;
+            num_trees++;
+        };
         while (status == S_RUNNING) {
             __syncwarp();
             if (phase == P_ENTER) {                      // grow(t), PHYNetwork.java:443-449
-                if (num_grow >= grow_limit || num_grow - grow_start >= step_quota) break;   // pause before counting the call
+                if (num_grow >= stop_at) break;          // pause before counting the call
                 if (tcount == n) {
                     if (rec_count >= rec_cap) break;     // record buffer full: pause
                     num_grow++;
-                    unsigned char *rp = records + (size_t)rec_count * record_bytes;
-                    if (lane == 0) {
-                        *reinterpret_cast<double *>(rp) = 0.0;
-                        *reinterpret_cast<long long *>(rp + 8) = num_trees;
-                        *reinterpret_cast<int *>(rp + 16) = 0;
-                        *reinterpret_cast<int *>(rp + 20) = 1;
-                    }
-                    if (lane < W) {
-                        unsigned a = 0, b = 0;
-                        for (int q = 3; q >= 0; q--) {
-                            const int i = q * W + lane;  // tree position i <-> treeNodes[i + 1]
-                            unsigned ab = 0xffu, bb = 0xffu;
-                            if (i < L) { ab = s.tn[i + 1]; bb = s.par[ab]; }
-                            a = (a << 8) | ab;
-                            b = (b << 8) | bb;
-                        }
-                        reinterpret_cast<unsigned *>(rp + 24)[lane] = a;
-                        reinterpret_cast<unsigned *>(rp + 24 + stride)[lane] = b;
-                    }
-                    rec_count++;
-                    num_trees++;
+                    record_tree();
                     if (depth == 0) { status = S_DONE; break; }      // only when the network is the root alone
                     depth--;
                     phase = P_AFTER_RETURN;
@@ -2254,7 +2262,7 @@ replay_kernel(const __grid_constant__ ReplayArgs a) {
         }
         return;                                          // the search is over: no state to save
     }
-    if (a.blob_in_smem) {
+    if (BS) {
         uint4 *bd = reinterpret_cast<uint4 *>(a.blob_dst);
         const uint4 *bs = reinterpret_cast<const uint4 *>(blob);
         for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
@@ -2973,8 +2981,10 @@ int run_reference_order(lichee_search *h, bool &completed) {
             unsigned char *rec = static_cast<unsigned char *>(h->b_rrec.p);
             a.records = rec; a.rec_cap = rec_cap;
             CK(cudaEventRecord(h->evk[0][0], h->stream));
-            if (small) replay_kernel<SPL, 1><<<1, kReplayThreads, smem, h->stream>>>(a);
-            else replay_kernel<SPL, 4><<<1, kReplayThreads, smem, h->stream>>>(a);
+            if (small && h->rblob_in_smem) replay_kernel<SPL, 1, true><<<1, kReplayThreads, smem, h->stream>>>(a);
+            else if (small) replay_kernel<SPL, 1, false><<<1, kReplayThreads, smem, h->stream>>>(a);
+            else if (h->rblob_in_smem) replay_kernel<SPL, 4, true><<<1, kReplayThreads, smem, h->stream>>>(a);
+            else replay_kernel<SPL, 4, false><<<1, kReplayThreads, smem, h->stream>>>(a);
             CK(cudaGetLastError());
             CK(cudaEventRecord(h->evk[0][1], h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -3428,10 +3438,14 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     if (h->device >= 0 && h->device < 64) {
         std::lock_guard<std::mutex> g(g_ctx.mu);
         if (!g_ctx.attrs2_set[h->device]) {
-            CKD(cudaFuncSetAttribute(replay_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
-            CKD(cudaFuncSetAttribute(replay_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
-            CKD(cudaFuncSetAttribute(replay_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
-            CKD(cudaFuncSetAttribute(replay_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
+            CKD(cudaFuncSetAttribute(replay_kernel<2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kReplaySmemMax));
             const int mx = kMaxN * 64 * (int)sizeof(double) + kMaxN;
             CKD(cudaFuncSetAttribute(score_ref_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
             CKD(cudaFuncSetAttribute(score_ref_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));

@@ -39,7 +39,7 @@ struct HostRecorder {
 }  // namespace
 
 // adj in node space; duplicates, self loops and edges into node 0 are dropped here like the library does.
-// stats: [0] trees, [1] numGrowCalls, [2] checks, [3] status (1 done, 2 tree cap, 3 grow cap), [4] compactions.
+// stats: [0] trees, [1] numGrowCalls, [2] checks, [3] status (1 done, 2 tree cap, 3 grow cap), [4] compactions, [5] checks at the last level.
 // Records up to `cap` trees (orders / parents: cap x n) in discovery order; `pause_every` > 0 makes the
 // recorder report "full" every that many trees so that pause/resume is exercised.
 extern "C" int replay_host_search(int n, int S, const int *adj_off, const int *adj_idx, const double *vaf,
@@ -61,12 +61,14 @@ extern "C" int replay_host_search(int n, int S, const int *adj_off, const int *a
     std::vector<unsigned char> blob(L.total);
     replay::init_blob(blob.data(), L, off.data(), idx.data(), max_grow, max_trees);
     replay::State s = replay::bind(blob.data(), L);
+    long long leaf_checks = 0;
     HostChecker chk{vaf, S, margin};
     HostRecorder rec{pause_every > 0 ? pause_every : cap, 0, n, orders, parents};
     for (;;) {
         for (;;) {
             const replay::Result r = replay::step(s, rec.room());
             if (r == replay::R_STOP) break;
+            if (r == replay::R_CHECK && s.h->tcount == n) leaf_checks++;
             if (r == replay::R_CHECK) s.h->ok = chk.check(s, s.h->cu, s.h->cv, s.h->ck, s.h->cprev) ? 1 : 0;
             if (r == replay::R_RECORD) rec.write(s, s.h->num_trees);
         }
@@ -77,5 +79,6 @@ extern "C" int replay_host_search(int n, int S, const int *adj_off, const int *a
     }
     stats[0] = s.h->num_trees; stats[1] = s.h->num_grow; stats[2] = s.h->num_checks; stats[3] = s.h->status;
     stats[4] = s.h->compactions;
+    stats[5] = leaf_checks;            // checkConstraint calls that add the LAST missing node
     return 0;
 }
