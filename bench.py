@@ -23,9 +23,11 @@ reference itself finishes: `bundled_datasets_build_search_ms` (identical output,
   e2e   : same, through the public API with HOST buffers: create (H2D) + run + ranked trees D2H
   roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
 
-N > 1 (torchrun, one rank per GPU): the frontier is cut at the first tree levels into N contiguous
-slices of the canonical order, each rank searches its slice (the tree cap applies per slice, so
-per-GPU work is fixed: weak scaling) and the N ranked lists are merged with one NCCL all_gather.
+N > 1 (torchrun, one rank per GPU): `value` stays the headline workload with the frontier cut at the first
+tree levels into N contiguous slices of the canonical order, each rank searching its slice under its own cap
+(per-GPU work fixed: weak scaling) and the N ranked lists merged with one NCCL all_gather.  `strong_scaling`
+is ONE exhaustive search shared by the N GPUs with dynamic work stealing (lichee_b200/dist.py), timed next to the
+same search on one GPU in the same run; the merged digest must equal the single-GPU digest.
 
 --impl reference: the literal CPU port of the reference search (oracle/, the JVM is absent from
 this image) on the same network, each step a bounded sample of grow() calls.
@@ -205,6 +207,59 @@ def named_shape_times(lichee_b200, adj, vaf, margin, args):
     return out
 
 
+def strong_scaling_leg(lichee_b200, torch, dist, rank, world, local, args):
+    """ONE exhaustive search (no cap binds) shared by all N GPUs with dynamic work stealing and one all_gather
+    (lichee_b200/dist.py), next to the same search on one GPU, timed in the same run: the merged top-s digest must
+    equal the single-GPU digest.  19 clusters x 9 samples, -c: 3.33e11 valid trees."""
+    from lichee_b200.dist import run_work_stealing
+    from lichee_b200.synth import make_instance
+    net, prm = make_instance(args.strong_clusters, args.strong_samples, seed=args.strong_seed)
+    vaf = np.ascontiguousarray(net.aaf, dtype=np.float64)
+    store = dist.distributed_c10d._get_default_store()
+    s = lichee_b200.LineageSearch(net.adj, vaf, prm.vaf_error_margin, num_save=args.save, max_num_trees=1 << 60,
+                                  max_num_grow_calls=1 << 62, device=local, ref_order_budget=-1)
+    n_slices = args.slices_per_gpu * world
+    dev = f"cuda:{local}"
+
+    def shared():
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        info = run_work_stealing(s, store, n_slices, key="bench/strong", device=dev)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()), info
+
+    shared()                                            # warm-up: level buffers come from the pool afterwards
+    t_n, info = shared()
+    digest_n = lichee_b200.top_list_sha256(s.trees(), with_seq=False)    # (sequence numbers are per slice)
+    mine = {"rank": rank, "slices": len(info["slices_claimed"]), "search_ms": round(1e3 * info["search_s"], 2),
+            "merge_ms": round(1e3 * info["merge_s"], 2), "redone": info["slices_redone"]}
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, mine)
+    t_1, digest_1, trees_1 = 0.0, None, 0
+    if rank == 0:                                       # the same search on one GPU (the others wait at the barrier)
+        s.run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = s.run()
+        torch.cuda.synchronize()
+        t_1 = time.perf_counter() - t0
+        digest_1 = lichee_b200.top_list_sha256(s.trees(), with_seq=False)
+        trees_1 = int(st.num_trees)
+    dist.barrier()
+    s.close()
+    if rank != 0:
+        return None
+    if digest_1 != digest_n or trees_1 != info["num_trees"]:
+        raise SystemExit(f"bench.py: the {world}-GPU search ({info['num_trees']} trees, {digest_n}) differs from the "
+                         f"single-GPU search ({trees_1} trees, {digest_1})")
+    return {"workload": f"synthetic {args.strong_samples}-sample {args.strong_clusters}-cluster complete network, exhaustive "
+                        f"(no cap binds), -s {args.save}: ONE search, {n_slices} slices claimed dynamically, one all_gather",
+            "scaling": "strong", "valid_trees": trees_1, "seconds_1gpu": t_1, "seconds_ngpu": t_n, "speedup": t_1 / t_n,
+            "efficiency": t_1 / t_n / world, "top_list_sha256": digest_n, "identical_to_1gpu": True, "per_rank": per_rank}
+
+
 def run_reference(args):
     """Reference arm: literal CPU port of PHYNetwork.grow on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -260,6 +315,11 @@ def main():
     ap.add_argument("--ref-grow-calls", type=int, default=1500000)
     ap.add_argument("--cpu-baseline-grow-calls", type=int, default=5000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-clusters", type=int, default=19)
+    ap.add_argument("--strong-samples", type=int, default=9)
+    ap.add_argument("--strong-seed", type=int, default=1)
+    ap.add_argument("--slices-per-gpu", type=int, default=16)
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -361,6 +421,10 @@ def main():
     checks_all, scored_all, launches_all, e2e_checks_all, eval_all, leaf_all, bounded_all = [float(x) for x in agg.tolist()]
     t_dev, t_e2e = [float(x) for x in tmax.tolist()]
 
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = strong_scaling_leg(lichee_b200, torch, dist, rank, world, local, args)
+
     if rank == 0:
         K = lichee_b200.SearchStats.KERNELS
         ms = [sum(s.kernel_ms[i] for s in stats) for i in range(5)]
@@ -419,6 +483,8 @@ def main():
                       "(it contains everything, host round trips and the merge included); device_ms_per_step and kernel_ms_per_step: "
                       "CUDA events on the library's own stream (rank 0)",
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
         if world == 1:
             # the same search with the lower bound switched off: every valid tree is scored
             os.environ["LICHEE_NO_PRUNE"] = "1"

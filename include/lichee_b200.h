@@ -133,11 +133,18 @@ int lichee_search_run(lichee_search *h);
  * (overrides part_rank/part_count).  With keep_ranked != 0 the ranked list, its threshold and the
  * statistics of the earlier slices on this handle are kept, so a GPU can claim slice after slice
  * from a counter shared by all ranks (lichee_b200/dist.py does it with the torch.distributed store).
- * Ties rank by (slice, seq), i.e. the same canonical order as one whole search; MAX_NUM_TREES
- * applies per slice. */
+ * Ties rank by (slice, seq), i.e. the same canonical order as one whole search.  Slices kept on one
+ * handle must be searched in ASCENDING order (LICHEE_ERR_STATE otherwise): a tree that ties with the worst
+ * held one is admitted only when it precedes it, which the kernels can assume of nothing that comes later.
+ * max_num_trees applies to the slice; ONE cap over the whole search (PHYNetwork.java:497, one spanningTrees
+ * list) is the caller's job: lichee_b200/dist.py gathers the per-slice counts, re-runs the slice the cap
+ * falls into with lichee_search_set_max_num_trees and drops the slices beyond it. */
 int lichee_search_run_slice(lichee_search *h, int32_t slice, int32_t n_slices, int32_t keep_ranked);
 /* Empty ranked list and zero statistics (a rank that claimed no slice still takes part in the merge). */
 int lichee_search_clear(lichee_search *h);
+
+/* Parameters.MAX_NUM_TREES for the runs that follow on this handle. */
+int lichee_search_set_max_num_trees(lichee_search *h, int64_t max_num_trees);
 
 int lichee_search_get_stats(const lichee_search *h, lichee_search_stats *out);
 

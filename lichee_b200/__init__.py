@@ -24,7 +24,7 @@ DEFAULT_REF_ORDER_BUDGET = 1 << 22
 
 EXPORTED_SYMBOLS = [
     "lichee_default_params", "lichee_search_create", "lichee_search_run", "lichee_search_run_slice",
-    "lichee_search_clear", "lichee_search_get_stats",
+    "lichee_search_clear", "lichee_search_get_stats", "lichee_search_set_max_num_trees",
     "lichee_search_get_tree", "lichee_search_get_trees", "lichee_record_bytes", "lichee_search_export_ranked",
     "lichee_search_merge_ranked", "lichee_search_get_order", "lichee_search_destroy",
     "lichee_get_lineage_trees", "lichee_release_cached_memory", "lichee_last_error", "lichee_version", "lichee_device_count",
@@ -85,6 +85,7 @@ def lib():
         L.lichee_search_run.argtypes = [ctypes.c_void_p]
         L.lichee_search_run_slice.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
         L.lichee_search_clear.argtypes = [ctypes.c_void_p]
+        L.lichee_search_set_max_num_trees.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         L.lichee_search_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(SearchStats)]
         L.lichee_search_get_tree.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]
@@ -181,13 +182,16 @@ class PHYTree:
     __str__ = toString
 
 
-def top_list_sha256(trees):
+def top_list_sha256(trees, with_seq=True):
     """SHA-256 of a ranked list: scores (f64) | seq (i64) | parents (i32), ranked order.  bench.py prints it for
-    every step and tests/golden/canonical_digests.json pins it for the benched shapes."""
+    every step and tests/golden/canonical_digests.json pins it for the benched shapes.  with_seq=False leaves the
+    sequence numbers out: in a sliced search they count from the start of the slice, so lists from different GPU
+    counts are compared on scores and trees."""
     import hashlib
     h = hashlib.sha256()
     h.update(np.array([t.errorScore for t in trees], dtype=np.float64).tobytes())
-    h.update(np.array([t.seq for t in trees], dtype=np.int64).tobytes())
+    if with_seq:
+        h.update(np.array([t.seq for t in trees], dtype=np.int64).tobytes())
     h.update(np.array([t.parent for t in trees], dtype=np.int32).tobytes())
     return h.hexdigest()
 
@@ -227,19 +231,31 @@ class LineageSearch:
         _ck(lib().lichee_search_run_slice(self._h, slice_id, n_slices, 1 if keep_ranked else 0))
         return self.stats()
 
-    def run_claimed(self, n_slices, claim):
+    def run_claimed(self, n_slices, claim, log=None):
         """Dynamic work stealing: `claim()` returns the next unclaimed slice id (or >= n_slices when
-        none is left); this GPU keeps one ranked list across everything it claims."""
+        none is left); this GPU keeps one ranked list across everything it claims.  `log`, a list, receives
+        (slice, valid trees of the slice, status of the slice) per claimed slice."""
         first = True
+        trees_before = 0
         while True:
             t = int(claim())
             if t >= n_slices:
                 break
-            self.run_slice(t, n_slices, keep_ranked=not first)
+            st = self.run_slice(t, n_slices, keep_ranked=not first)
+            if log is not None:
+                log.append((t, int(st.num_trees) - trees_before, int(st.status)))
+            trees_before = int(st.num_trees)
             first = False
         if first:                       # nothing claimed: an empty ranked list that can still be exported
             _ck(lib().lichee_search_clear(self._h))
         return not first
+
+    def clear(self):
+        _ck(lib().lichee_search_clear(self._h))
+
+    def set_max_num_trees(self, v):
+        _ck(lib().lichee_search_set_max_num_trees(self._h, int(v)))
+        self.params.max_num_trees = int(v)
 
     def stats(self):
         st = SearchStats()

@@ -2414,6 +2414,7 @@ struct lichee_search {
     DevNet net{};
     size_t smem = 0, smem_leaf = 0;
     // reference-order mode (lichee_replay.cuh)
+    int last_slice = -1;                     // highest slice searched into the list kept on this handle (keep_ranked)
     bool cyclic = false;                     // the network has a directed cycle: only the replay can search it
     bool ref_result = false;                 // the ranked list on the host came from the replay (records of 2 x stride bytes)
     replay::Layout rlay{};
@@ -3462,6 +3463,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
 int lichee_search_run(lichee_search *h) {
     if (!h) { set_err("null handle"); return LICHEE_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
+    h->last_slice = -1;
     const int rc = run_whole(h);
     if (rc == LICHEE_OK) h->ran = true;
     return rc;
@@ -3473,10 +3475,17 @@ int lichee_search_run_slice(lichee_search *h, int32_t slice, int32_t n_slices, i
     if (keep_ranked && !h->ran) { set_err("keep_ranked needs an earlier run on this handle"); return LICHEE_ERR_STATE; }
     if (h->cyclic) { set_err("constraint network has a directed cycle: a sliced (canonical) search needs a DAG"); return LICHEE_ERR_CYCLIC; }
     if (keep_ranked && h->ref_result) { set_err("keep_ranked: the list on this handle is a reference-order result"); return LICHEE_ERR_STATE; }
+    // A tree whose score EQUALS the worst held one is admitted only if it precedes it in the canonical order; the
+    // kernels decide that with `score < tau`, which is right exactly when every tree still to come follows the held
+    // ones, i.e. when slices are taken in ascending order (a shared counter hands them out that way).
+    if (keep_ranked && slice <= h->last_slice) {
+        set_err("keep_ranked: slice %d after slice %d -- slices kept on one handle must be searched in ascending order", slice, h->last_slice);
+        return LICHEE_ERR_STATE;
+    }
     CK(cudaSetDevice(h->device));
     h->ref_result = false;
     const int rc = h->SP == 32 ? run_search<1>(h, slice, n_slices, keep_ranked != 0) : run_search<2>(h, slice, n_slices, keep_ranked != 0);
-    if (rc == LICHEE_OK) { h->ran = true; h->stats.status |= LICHEE_STATUS_CANONICAL_ORDER; }
+    if (rc == LICHEE_OK) { h->ran = true; h->stats.status |= LICHEE_STATUS_CANONICAL_ORDER; h->last_slice = slice; }
     return rc;
 }
 
@@ -3487,12 +3496,20 @@ int lichee_search_clear(lichee_search *h) {
     CK(cudaGetLastError());
     h->flip = 0;
     h->ref_result = false;
+    h->last_slice = -1;
     h->stats = lichee_search_stats{};
     h->stats.num_grow_calls = 0;
     h->stats.status = LICHEE_STATUS_CANONICAL_ORDER;
     const int rc = fetch_top(h);
     if (rc == LICHEE_OK) h->ran = true;
     return rc;
+}
+
+int lichee_search_set_max_num_trees(lichee_search *h, int64_t max_num_trees) {
+    if (!h || max_num_trees < 1) { set_err("invalid argument"); return LICHEE_ERR_INVALID; }
+    h->prm.max_num_trees = max_num_trees;
+    reinterpret_cast<replay::Header *>(h->rblob0)->max_trees = max_num_trees;
+    return LICHEE_OK;
 }
 
 int lichee_search_get_stats(const lichee_search *h, lichee_search_stats *out) {

@@ -47,7 +47,7 @@ def main():
         store = dist.distributed_c10d._get_default_store()
     net, prm = make_instance(args.clusters, args.samples, args.seed)
     s = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=args.save, device=local,
-                                  max_num_trees=1 << 60, max_num_grow_calls=1 << 62)
+                                  max_num_trees=1 << 60, max_num_grow_calls=1 << 62, ref_order_budget=-1)
     n_slices = args.slices_per_gpu * world
     times = []
     for rep in range(args.repeat):

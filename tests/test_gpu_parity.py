@@ -257,7 +257,7 @@ def test_work_stealing_slices_give_the_whole_search(built):
     a = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
     b = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
     c = lichee_b200.LineageSearch(net.adj, net.aaf, prm.vaf_error_margin, num_save=40, max_num_trees=10**9, ref_order_budget=-1)
-    order_a, order_b = iter([11, 0, 5, 7, 2, T]), iter([3, 10, 1, 9, 8, 6, 4, T])
+    order_a, order_b = iter([0, 2, 5, 7, 11, T]), iter([1, 3, 4, 6, 8, 9, 10, T])       # (ascending on each handle)
     a.run_claimed(T, lambda: next(order_a))
     b.run_claimed(T, lambda: next(order_b))
     assert not c.run_claimed(T, lambda: T)                  # a rank that found nothing left to claim
@@ -269,6 +269,31 @@ def test_work_stealing_slices_give_the_whole_search(built):
         assert [t.parent for t in m] == [t.parent for t in trees]
         assert [t.errorScore for t in m] == [t.errorScore for t in trees]
         h.close()
+
+
+def test_slices_with_tied_scores_and_the_ascending_order_rule(built):
+    """Real -c data is dominated by zero-error ties (RK26 -c: 99 of the top 100 scores tie).  Ties rank by (slice,
+    seq); a kept list admits a tying tree only if it precedes the held ones, so slices kept on one handle must be
+    searched in ascending order -- anything else is refused."""
+    import lichee_b200
+    e = [x for x in _networks() if x["dataset"] == "ccRCC/RK26.txt" and x["complete_edges"] and x["clustering"] == "single"][0]
+    adj, vaf, margin = e["adj"], np.array(e["aaf"]), e["vaf_error_margin"]
+    whole, trees, _ = gpu_search(adj, vaf, margin, 100, max_num_trees=10**9)
+    assert len({t.errorScore for t in trees}) < 10                      # massive ties
+    T = 9
+    a = lichee_b200.LineageSearch(adj, vaf, margin, num_save=100, max_num_trees=10**9, ref_order_budget=-1)
+    b = lichee_b200.LineageSearch(adj, vaf, margin, num_save=100, max_num_trees=10**9, ref_order_budget=-1)
+    ia, ib = iter([0, 3, 4, 8, T]), iter([1, 2, 5, 6, 7, T])
+    a.run_claimed(T, lambda: next(ia))
+    b.run_claimed(T, lambda: next(ib))
+    assert a.stats().num_trees + b.stats().num_trees == whole["num_trees"]
+    recs = np.concatenate([a.export_ranked(), b.export_ranked()])
+    a.merge_ranked(recs, 2)
+    assert [(t.errorScore, t.parent) for t in a.trees()] == [(t.errorScore, t.parent) for t in trees]
+    with pytest.raises(lichee_b200.LicheeError) as err:                 # slice 2 after slice 7 on the same list
+        b.run_slice(2, T, keep_ranked=True)
+    assert err.value.code == -6
+    a.close(); b.close()
 
 
 @pytest.mark.parametrize("n_clusters,n_samples,cap", [(40, 20, 1 << 22), (120, 64, 1 << 22)])
