@@ -117,6 +117,7 @@ struct TopMeta {             // device-resident state of the ranked list
     unsigned long long next_run; // work queue of the current leaf launch: next unclaimed run of items
     unsigned long long n_bounded; // items of the current leaf launch whose trees were excluded by the lower bound
     unsigned long long n_eval;   // trees of the current leaf launch whose total was computed
+    unsigned long long kmin, kmax; // smallest / largest score bits among the candidates of the current leaf launch
 };
 
 struct ScanOut {             // written by the scan, read back by the host once per chunk
@@ -1184,6 +1185,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     double tau;
     const double tmax = admit_bound(meta, num_save, full, tau);
     unsigned long long my_valid = 0, my_eval = 0;
+    unsigned long long kmn = ~0ull, kmx = 0ull;   // score bits of the candidates this thread wrote
     unsigned my_bounded = 0;
     // candidate slots are reserved kCandBatch at a time per warp (one atomic on the shared counter per batch,
     // not per tree: in a good region millions of trees beat a stale threshold within one launch); slots a
@@ -1411,6 +1413,9 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
                         const unsigned q = g * 32 + lane;
                         Cand c;
                         if (!full || score < tau) {
+                            const unsigned long long kb = (unsigned long long)__double_as_longlong(score);
+                            kmn = kb < kmn ? kb : kmn;
+                            kmx = kb > kmx ? kb : kmx;
                             c.score = score; c.seq = 0; c.part = part;
                             c.origin = (unsigned)(item_base + it);
                             c.pstar = q | ((unsigned)cidx_s[q] << 8);
@@ -1434,6 +1439,13 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
     if (lane == 0 && my_bounded) atomicAdd(&meta->n_bounded, (unsigned long long)my_bounded);
     if (lane == 0 && my_eval) atomicAdd(&meta->n_eval, my_eval);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(kFull, kmn, d), b = __shfl_xor_sync(kFull, kmx, d);
+        kmn = a < kmn ? a : kmn;
+        kmx = b > kmx ? b : kmx;
+    }
+    if (lane == 0 && kmn <= kmx) { atomicMin(&meta->kmin, kmn); atomicMax(&meta->kmax, kmx); }
 }
 
 // Gives every candidate its canonical sequence number (rank among the valid trees) now that the
@@ -1627,7 +1639,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
         meta->n_valid = 0;
-        meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
+        meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull;
     }
 }
 
@@ -1734,7 +1746,140 @@ radix_compact(const Cand *__restrict__ cands, long long m, RadixState *st, Cand 
     }
 }
 
-__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; }
+// Radix pre-selection, second form (the one the last-level chunks use): the candidates of a burst agree in their
+// leading score bits (scores of neighbouring trees agree to five digits), so byte-wise passes from the top spend
+// most launches on bytes that cannot separate anything.  leaf_kernel keeps the smallest and largest candidate key;
+// the passes start at the first bit where the two differ, take 12 bits at a time (4096-bin histogram in shared
+// memory) and stop as soon as the candidates at or below the bucket of the k-th smallest key fit the rank-merge
+// tile.  More trees with exactly the threshold score than the tile holds (common: whole families of trees tie)
+// are separated by their sequence numbers the same way, starting at the first bit in which the sequence numbers
+// of the chunk differ: typically five or six passes over the candidates instead of sixteen.
+struct Radix12State {
+    unsigned long long prefix[2];   // decided high bits of the threshold key: [0] score bits, [1] seq
+    unsigned long long k;           // rank still to find inside the current bucket
+    unsigned long long below;       // candidates below the current bucket
+    unsigned long long kept;        // candidates compacted
+    unsigned long long thresh[2];   // done: keep every key (score bits, seq) <= thresh
+    int word;                       // 0: digits of the score, 1: digits of seq among the candidates with exactly the threshold score
+    int shift, width;               // current digit: bits [shift, shift + width) of the current word; shift < 0: none left
+    int seq_rest;                   // low bits in which the sequence numbers of this chunk differ
+    unsigned done, blocks_done;
+    unsigned hist[4096];
+};
+
+__global__ void radix12_init(Radix12State *st, const TopMeta *meta, unsigned long long k, unsigned long long seq_lo,
+                             unsigned long long seq_hi) {
+    if (threadIdx.x == 0) {
+        const unsigned long long kmin = meta->kmin, kmax = meta->kmax;
+        st->k = k; st->below = 0; st->kept = 0; st->blocks_done = 0; st->done = 0; st->thresh[0] = st->thresh[1] = 0;
+        st->word = 0;
+        const unsigned long long sx = seq_lo ^ seq_hi;
+        const int slead = sx ? __clzll((long long)sx) : 64;
+        st->seq_rest = 64 - slead;
+        st->prefix[1] = slead == 0 ? 0ull : slead == 64 ? seq_lo : seq_lo & ~(~0ull >> slead);
+        if (kmin > kmax) {                              // no candidate at all
+            st->done = 1; st->thresh[0] = st->thresh[1] = ~0ull; st->prefix[0] = 0; st->shift = -1; st->width = 0;
+        } else {
+            const unsigned long long x = kmin ^ kmax;
+            const int lead = x ? __clzll((long long)x) : 64;
+            const int rest = 64 - lead;                 // low bits in which the candidate scores differ
+            st->prefix[0] = lead == 0 ? 0ull : lead == 64 ? kmin : kmin & ~(~0ull >> lead);
+            if (rest == 0) {                            // one score: straight to the sequence numbers
+                st->word = 1;
+                st->width = st->seq_rest < 12 ? st->seq_rest : 12;
+                st->shift = st->seq_rest == 0 ? -1 : st->seq_rest - st->width;
+            } else {
+                st->width = rest < 12 ? rest : 12;
+                st->shift = rest - st->width;
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) st->hist[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+radix12_pass(const Cand *__restrict__ cands, long long m, Radix12State *st, unsigned tile) {
+    __shared__ unsigned h[4096];
+    __shared__ unsigned part[256];
+    __shared__ bool last;
+    if (st->done || st->shift < 0) return;              // uniform for the whole grid
+    const int word = st->word, shift = st->shift, width = st->width, hi = shift + width;
+    const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
+    const unsigned dmask = (1u << width) - 1u;
+    for (int i = threadIdx.x; i < 4096; i += 256) h[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const Cand c = cands[i];
+        if (c.pad) continue;
+        const unsigned long long k0 = (unsigned long long)__double_as_longlong(c.score), k1 = (unsigned long long)c.seq;
+        if (word == 0) {
+            if (hi >= 64 || (k0 >> hi) == (p0 >> hi)) atomicAdd(&h[(unsigned)(k0 >> shift) & dmask], 1u);
+        } else if (k0 == p0 && (hi >= 64 || (k1 >> hi) == (p1 >> hi))) {
+            atomicAdd(&h[(unsigned)(k1 >> shift) & dmask], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += 256) if (h[i]) atomicAdd(&st->hist[i], h[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    unsigned mine = 0;                                   // 16 bins per thread, then a scan of the 256 partial sums
+    for (int j = 0; j < 16; j++) { const unsigned v = *(volatile unsigned *)&st->hist[threadIdx.x * 16 + j]; h[threadIdx.x * 16 + j] = v; mine += v; }
+    part[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long k = st->k, run = 0;
+        int g = 0;
+        for (; g < 256; g++) { if (run + part[g] >= k) break; run += part[g]; }
+        if (g == 256) {                                 // fewer than k candidates in the bucket: keep everything
+            st->done = 1; st->thresh[0] = st->thresh[1] = ~0ull;
+        } else {
+            int b = g * 16;
+            for (;; b++) { if (run + h[b] >= k) break; run += h[b]; }
+            const unsigned long long pre = (word == 0 ? p0 : p1) | ((unsigned long long)b << shift);
+            st->prefix[word] = pre; st->k = k - run; st->below += run;
+            const unsigned long long low = shift > 0 ? (1ull << shift) - 1ull : 0ull;
+            if (st->below + h[b] <= (unsigned long long)tile) {
+                st->done = 1;
+                if (word == 0) { st->thresh[0] = pre | low; st->thresh[1] = ~0ull; }
+                else { st->thresh[0] = p0; st->thresh[1] = pre | low; }
+            } else if (shift > 0) {
+                const int w = shift < 12 ? shift : 12;
+                st->width = w; st->shift = shift - w;
+            } else if (word == 0) {
+                // more trees with exactly the threshold score than the tile holds: the sequence numbers decide
+                st->word = 1;
+                st->width = st->seq_rest < 12 ? st->seq_rest : 12;
+                st->shift = st->seq_rest == 0 ? -1 : st->seq_rest - st->width;
+            } else {
+                st->shift = -1;                         // (keys are unique: not reached)
+            }
+        }
+        st->blocks_done = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += 256) st->hist[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+radix12_compact(const Cand *__restrict__ cands, long long m, Radix12State *st, Cand *__restrict__ out, long long out_cap) {
+    if (!st->done) return;
+    const unsigned long long t0 = st->thresh[0], t1 = st->thresh[1];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const Cand c = cands[i];
+        if (c.pad) continue;
+        const unsigned long long k0 = (unsigned long long)__double_as_longlong(c.score), k1 = (unsigned long long)c.seq;
+        if (k0 < t0 || (k0 == t0 && k1 <= t1)) {
+            const unsigned long long slot = atomicAdd(&st->kept, 1ull);
+            if ((long long)slot < out_cap) out[slot] = c;
+        }
+    }
+}
+
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -1742,7 +1887,7 @@ __global__ void init_meta(TopMeta *meta) {
     meta->tau = INFINITY;
     meta->n_cand = 0;
     meta->n_valid = 0;
-    meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
+    meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull;
 }
 
 // unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
@@ -1918,7 +2063,7 @@ replay_kernel(const __grid_constant__ ReplayArgs a) {
         if (a.first && threadIdx.x == 0) {
             TopMeta *meta = a.meta;
             meta->count = 0; meta->pad = 0; meta->tau = INFINITY; meta->n_cand = 0; meta->n_valid = 0;
-            meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
+            meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull;
         }
         if (threadIdx.x == 0) fuse_count_s = -1;
     }
@@ -2392,7 +2537,7 @@ struct lichee_search {
     std::vector<long long> head, tail;
     long long cap = 0;                       // upper bound on items per level buffer
     long long cand_cap = 0;                  // upper bound on candidates one last-level launch may append
-    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_cands[2], b_top[2], b_tree[2];
+    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_radix12, b_cands[2], b_top[2], b_tree[2];
     DevBuf b_mask2, b_mask3, b_flag;         // level L-2 chunks: "v and u" mask, "u without v" mask, bounded flag
     DevBuf b_lmask, b_lcnt;                  // last level, parallel to its item buffer: pass mask, count | flags
     uint4 sok_last{};                        // static pass mask of the last node (n == 2: the only item's mask)
@@ -2528,6 +2673,44 @@ int run_radix_select(lichee_search *h, long long &m, bool &used) {
     CK(cudaStreamSynchronize(h->stream));
     if (kept > (unsigned long long)kSelTile) return LICHEE_OK;       // massive ties: not usable
     m = (long long)kept;
+    used = true;
+    return LICHEE_OK;
+}
+
+// The 12-bit form for last-level chunks (leaf_kernel recorded the key range in the meta block).  Falls back to
+// run_radix_select when equal scores overflow the tile.
+int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq_lo, long long seq_hi) {
+    used = false;
+    if (ensure(h, h->b_radix12, sizeof(Radix12State)) != LICHEE_OK ||
+        ensure(h, h->b_cands[1], sizeof(Cand) * (size_t)kSelTile) != LICHEE_OK)
+        return LICHEE_ERR_CUDA;
+    Radix12State *st = static_cast<Radix12State *>(h->b_radix12.p);
+    const int grid = (int)std::min<long long>((m + 255) / 256, 148 * 8);
+    radix12_init<<<1, 256, 0, h->stream>>>(st, h->d_meta(), (unsigned long long)h->prm.num_save, (unsigned long long)seq_lo,
+                                           (unsigned long long)seq_hi);
+    h->stats.num_launches++;
+    h->stats.kernel_launches[LICHEE_K_SELECT]++;
+    struct { unsigned long long kept; int shift; unsigned done; } rd{};
+    for (int round = 0; round < 2; round++) {           // 6 + 6 digits cover the 128 key bits; finished passes return at once
+        for (int p = 0; p < 6; p++) radix12_pass<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, (unsigned)kSelTile);
+        radix12_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, h->d_cands(1), (long long)kSelTile);
+        CK(cudaGetLastError());
+        h->stats.num_launches += 7;
+        h->stats.kernel_launches[LICHEE_K_SELECT] += 7;
+        CK(cudaMemcpyAsync(&rd.kept, &st->kept, sizeof(rd.kept), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&rd.shift, &st->shift, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&rd.done, &st->done, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (rd.done || rd.shift < 0) break;
+    }
+    if (getenv("LICHEE_DEBUG")) {
+        Radix12State hs;
+        cudaMemcpy(&hs, st, offsetof(Radix12State, hist), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "radix12: m=%lld done=%u word=%d shift=%d kept=%llu below=%llu k=%llu thresh=%016llx/%llu\n", m, hs.done, hs.word,
+                hs.shift, hs.kept, hs.below, hs.k, hs.thresh[0], hs.thresh[1]);
+    }
+    if (!rd.done || rd.kept > (unsigned long long)kSelTile) return run_radix_select(h, m, used);
+    m = (long long)rd.kept;
     used = true;
     return LICHEE_OK;
 }
@@ -2864,7 +3047,8 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 st.num_launches++;
                 int src = 0;
                 bool radix = false;
-                if (m > kSelTile && run_radix_select(h, m, radix) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                if (m > kSelTile && run_radix12_select(h, m, radix, seq_base, seq_base + std::max<long long>(leaf_total, 1) - 1) != LICHEE_OK)
+                    return LICHEE_ERR_CUDA;
                 if (radix) src = 1;
                 else if (run_tournament(h, m, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 if (run_select(h, h->d_cands(src), m, h->level(lv), 0, nullptr, 0) != LICHEE_OK) return LICHEE_ERR_CUDA;
@@ -3145,6 +3329,7 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_mask); give_back(h, h->b_cnt); give_back(h, h->b_off); give_back(h, h->b_tile);
     give_back(h, h->b_small);
     give_back(h, h->b_radix);
+    give_back(h, h->b_radix12);
     give_back(h, h->b_slab);
     give_back(h, h->b_sched);
     give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag);
