@@ -31,7 +31,7 @@ int main(int argc, char **argv) {
         if (o == "-build") build = true;
         else if (o == "-i") a.inputFileName = need(i);
         else if (o == "-o") a.outputFileName = need(i);
-        else if (o == "-cp") { p.CP = true; p.VAF_MAX = 1.0; p.MAX_ALLOWED_VAF = 1.0; }
+        else if (o == "-cp") p.CP = true;
         else if (o == "-sampleProfile") p.INPUT_FORMAT = lichee::Parameters::SNV_WITH_PROFILE;
         else if (o == "-n" || o == "-normal") { a.normalSampleId = std::atoi(need(i)); haveN = true; }
         else if (o == "-clustersFile") a.clustersFileName = need(i);
@@ -63,6 +63,8 @@ int main(int argc, char **argv) {
         else if (o == "-h" || o == "-help") { usage(); return 0; }
         else { std::cerr << "Unrecognized option: " << argv[i] << "\n"; usage(); return -1; }
     }
+    // -cp wins over -maxVAFValid wherever it stands on the command line (LineageEngine.java:348-376 applies it last)
+    if (p.CP) { p.VAF_MAX = 1.0; p.MAX_ALLOWED_VAF = 1.0; }
     if (a.inputFileName.empty()) { std::cerr << "Required parameter: input file path [-i]\n"; usage(); return -1; }
     if (a.outputFileName.empty()) a.outputFileName = a.inputFileName + ".trees.txt";
     const bool profile = p.INPUT_FORMAT == lichee::Parameters::SNV_WITH_PROFILE;

@@ -89,3 +89,35 @@ def test_cli_network_adjustment_loop(built, tmp_path):
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0
     assert "Found 0 valid tree(s)" in r.stderr and "after network adjustments" in r.stderr
+
+
+def test_cli_cyclic_constraint_network(built, tmp_path):
+    """Three clusters of ONE group whose pairwise centroid differences stay inside -e in one direction only form
+    a directed 3-cycle (checkAndAddEdge, PHYNetwork.java:185-232; with -clustersFile no collapse step runs,
+    LineageEngine.java:95-99).  The reference's Gabow-Myers search takes any digraph; through the CLI the library
+    searches it with the reference-order replay and writes the reference's trees (literal port, oracle/)."""
+    import oracle
+    from conftest import parse_network_dump as parse_dump
+    c = (0.20, 0.20, 0.30)
+    a = (c[0] + 0.06, c[1] + 0.06, c[2] - 0.12)
+    b = (a[0] - 0.15, a[1] + 0.09, a[2] + 0.06)
+    rows = [a, a, b, b, c, c]
+    snv = "#chr\tposition\tdescription\tNormal\tA\tB\tC\n" + "".join(
+        f"1\t{i}\ts{i}\t0.0\t{r[0]!r}\t{r[1]!r}\t{r[2]!r}\n" for i, r in enumerate(rows, 1))
+    clu = "".join(f"0111\t0.0\t{r[0]!r}\t{r[1]!r}\t{r[2]!r}\t{2 * k + 1},{2 * k + 2}\n" for k, r in enumerate((a, b, c)))
+    (tmp_path / "in.txt").write_text(snv)
+    (tmp_path / "c.txt").write_text(clu)
+    base = [CLI, "-build", "-i", str(tmp_path / "in.txt"), "-clustersFile", str(tmp_path / "c.txt"), "-n", "0",
+            "-maxVAFAbsent", "0.005", "-minVAFPresent", "0.005", "-e", "0.1", "-s", "10"]
+    subprocess.run(base + ["-dumpNetwork", str(tmp_path / "net.txt")], check=True, capture_output=True)
+    tags, sizes, aaf, adj = parse_dump(tmp_path / "net.txt")
+    inner = {(u, v) for u in range(1, 4) for v in adj[u]}
+    assert len(inner) == 3 and all(any((v, w) in inner for w in range(1, 4)) for (_, v) in inner)     # a -> b -> c -> a
+    r = subprocess.run(base + ["-o", str(tmp_path / "out.trees.txt")], check=True, capture_output=True, text=True)
+    ref = oracle.search(adj, np.array(aaf), 0.1, top_s=10)
+    assert ref["n_trees"] > 0 and f"Found {ref['n_trees']} valid tree" in r.stderr
+    got, _ = parse_trees(tmp_path / "out.trees.txt")
+    assert len(got) == len(ref["scores"])
+    for (edges, score), sc, par in zip(got, ref["scores"], ref["parents"]):
+        assert score == sc
+        assert sorted(edges) == sorted((int(par[v]), v) for v in range(1, len(par)))
