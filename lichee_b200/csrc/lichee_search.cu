@@ -2007,6 +2007,8 @@ constexpr int kReplaySmemMax = 208 * 1024;  // dynamic shared memory the replay 
 constexpr int kReplayRecCap = 1 << 15;       // trees one replay launch may record before the batch is scored and merged
 constexpr size_t kPinnedBlob = 256 * 1024;   // pinned: initial replay state (largest layout: 128 nodes, 64 samples, 16256 edges)
 constexpr size_t kPinnedResult = (size_t)LICHEE_MAX_SAVE * (32 + 2 * 128);   // pinned: Cand | tree bytes of a fused result
+constexpr size_t kPinnedVaf = (size_t)LICHEE_MAX_NODES * 64 * 8;              // pinned: centroid matrix in row space (what the replay stages)
+constexpr size_t kPinnedDesc = 256;                                           // pinned: rows in descending node id
 constexpr int kFuseMax = 1024;               // a search with at most this many trees is scored and ranked by the replay launch itself
 
 struct FuseKey { double score; unsigned idx, pad; };
@@ -2566,6 +2568,10 @@ struct lichee_search {
     unsigned char *h_big = nullptr;          // pinned: [initial state of getLineageTrees() | fused result block]
     unsigned char *rblob0 = nullptr;         // = h_big: the initial state, read by the first replay launch of every run
     unsigned char *h_result = nullptr;       // = h_big + kPinnedBlob
+    double *p_vaf = nullptr;                 // pinned copy of the centroid matrix (row space): the replay reads it from here
+    uint8_t *p_desc = nullptr;               // pinned copy of desc_rows
+    std::vector<unsigned char> tables;       // [vaf | leaf_static | static_ok | cand | ncand | desc]: uploaded by the first search that needs them
+    bool tables_on_device = false;
     bool rblob_in_smem = false;
     DevBuf b_rblob, b_rrec;                  // state blob (device copy), record buffer
     ReplayOut *h_rout = nullptr;             // pinned
@@ -2632,6 +2638,35 @@ int launch_scan(lichee_search *h, const unsigned *cnt, long long n_items, unsign
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
+    return LICHEE_OK;
+}
+
+// Device-side set-up of everything beyond the replay's first launch: the network tables, the level slab, the
+// scheduler block and the double-buffered ranked list.  Stream-ordered; called by the first search that needs it.
+int upload_tables(lichee_search *h) {
+    if (h->tables_on_device) return LICHEE_OK;
+    const int Lp = std::max(1, h->L);
+    CK(cudaMemcpyAsync(h->b_net.p, h->tables.data(), h->tables.size(), cudaMemcpyHostToDevice, h->stream));
+    {
+        // every level starts as a view of kNarrowCap items into one slab; a level that needs more gets
+        // its own buffer from the pool (ensure)
+        const size_t per = (size_t)kNarrowCap * h->stride;
+        if (ensure(h, h->b_slab, per * Lp) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        for (int lv = 0; lv < Lp; lv++) {
+            if (!h->b_level[lv].p || h->b_level[lv].view) {
+                h->b_level[lv].p = static_cast<char *>(h->b_slab.p) + per * lv;
+                h->b_level[lv].bytes = per;
+                h->b_level[lv].view = true;
+            }
+        }
+    }
+    if (ensure(h, h->b_sched, sizeof(Sched)) != LICHEE_OK) return LICHEE_ERR_CUDA;
+    for (int i = 0; i < 2; i++) {
+        if (ensure(h, h->b_top[i], sizeof(Cand) * LICHEE_MAX_SAVE) != LICHEE_OK ||
+            ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * 2 * h->stride) != LICHEE_OK)
+            return LICHEE_ERR_CUDA;
+    }
+    h->tables_on_device = true;
     return LICHEE_OK;
 }
 
@@ -2776,6 +2811,7 @@ int harvest_events(lichee_search *h, int set) {
 template <int SPL>
 int run_search(lichee_search *h, int R, int P, bool keep) {
     const int L = h->L;
+    if (upload_tables(h) != LICHEE_OK) return LICHEE_ERR_CUDA;
     lichee_search_stats &st = h->stats;
     const lichee_search_stats before = st;
     st = lichee_search_stats{};
@@ -2995,10 +3031,12 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             if (!list_full) cand_limit = std::min<long long>(cand_limit, 1 << 17);
             if (launch_scan(h, lcnt, B, (unsigned long long)cand_limit, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
-            const int grid = grid_for(B);
+            int grid = grid_for(B);
             // runs of items are claimed dynamically by the warps, in 32-item blocks (a bounded item costs a
             // few instructions, an evaluated one hundreds)
             int run_len = (int)std::min<long long>(256, std::max<long long>(32, (B / ((long long)grid * kWarpsPerBlock * 4) + 31) / 32 * 32));
+            if (const char *e = getenv("LICHEE_LEAF_GRID")) grid = std::min(grid, atoi(e));
+            if (const char *e = getenv("LICHEE_LEAF_RUN")) run_len = std::min(run_len, std::max(32, atoi(e)));
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, h->d_scan(), h->head[lv], lcnt, R, h->d_meta(), h->prm.num_save,
                 h->d_cands(0), cand_cap, run_len);
@@ -3151,12 +3189,12 @@ int run_reference_order(lichee_search *h, bool &completed) {
         a.blob_src = h->rblob0;                                // pinned initial state, read by the kernel itself
         a.blob_dst = static_cast<unsigned char *>(h->b_rblob.p);
         a.blob_in_smem = h->rblob_in_smem ? 1 : 0;
-        a.vaf = h->net.vaf; a.S = h->S; a.L = h->L; a.stride = h->stride; a.margin = h->prm.vaf_error_margin;
+        a.vaf = h->p_vaf; a.S = h->S; a.L = h->L; a.stride = h->stride; a.margin = h->prm.vaf_error_margin;   // (pinned: staged by the kernel)
         a.record_bytes = rb;
         a.step_quota = 1ll << 22; a.grow_limit = budget;
         a.out = h->h_rout;                                     // pinned: read after the synchronize, no copy
         a.first = 1; a.fuse = 1; a.num_save = h->prm.num_save;
-        a.meta = h->d_meta(); a.desc_rows = h->net.desc_rows; a.result = h->h_result;
+        a.meta = h->d_meta(); a.desc_rows = h->p_desc; a.result = h->h_result;
         const size_t smem = (size_t)h->n * h->SP * sizeof(double) + (h->rblob_in_smem ? h->rlay.total : 0);
         const bool small = h->n <= 32;
         // record buffer: small for the first launch (most real searches end inside it), full size afterwards
@@ -3184,6 +3222,7 @@ int run_reference_order(lichee_search *h, bool &completed) {
             st.kernel_bytes[LICHEE_K_CHECK] += (long long)m * rb;
             if (h->h_rout->fused) { fused = true; break; }
             a.first = 0; a.fuse = 0; a.blob_src = a.blob_dst;
+            if (upload_tables(h) != LICHEE_OK) return LICHEE_ERR_CUDA;     // (scoring and merging use the device-resident tables and lists)
             if (m > 0) {
                 // score the batch (one warp per tree) and merge it into the ranked list
                 if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)std::max(m, kSelTile)) != LICHEE_OK) return LICHEE_ERR_CUDA;
@@ -3453,7 +3492,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
             CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
             for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
             CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta) + sizeof(Sched) + sizeof(ReplayOut)));
-            CKD(cudaMallocHost(&h->h_big, kPinnedBlob + kPinnedResult));
+            CKD(cudaMallocHost(&h->h_big, kPinnedBlob + kPinnedResult + kPinnedVaf + kPinnedDesc));
         }
     }
     const int Lp = std::max(1, h->L);
@@ -3537,39 +3576,31 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     for (int k = 0; k < n; k++) desc[k] = (uint8_t)qof[n - 1 - k];
     CKE(ensure(h, h->b_net, o_desc + desc.size()));
     char *nb = static_cast<char *>(h->b_net.p);
-    CKD(cudaMemcpyAsync(nb, vp.data(), vp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(nb + o_ls, lstat.data(), lstat.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(nb + o_sok, sok.data(), sok.size() * sizeof(uint4), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(nb + o_cand, cd.data(), cd.size(), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(nb + o_ncand, nc.data(), nc.size(), cudaMemcpyHostToDevice, h->stream));
-    CKD(cudaMemcpyAsync(nb + o_desc, desc.data(), desc.size(), cudaMemcpyHostToDevice, h->stream));
+    // The tables go to the device with the first search that reads them (upload_tables): a search that ends inside
+    // the reference-order replay -- every search of a real data set -- only needs the matrix and desc_rows, which
+    // the replay kernel stages straight from pinned host memory.
+    h->tables.resize(o_desc + desc.size());
+    memcpy(h->tables.data(), vp.data(), vp.size() * sizeof(double));
+    memcpy(h->tables.data() + o_ls, lstat.data(), lstat.size() * sizeof(double));
+    memcpy(h->tables.data() + o_sok, sok.data(), sok.size() * sizeof(uint4));
+    memcpy(h->tables.data() + o_cand, cd.data(), cd.size());
+    memcpy(h->tables.data() + o_ncand, nc.data(), nc.size());
+    memcpy(h->tables.data() + o_desc, desc.data(), desc.size());
+    h->p_vaf = reinterpret_cast<double *>(h->h_big + kPinnedBlob + kPinnedResult);
+    h->p_desc = h->h_big + kPinnedBlob + kPinnedResult + kPinnedVaf;
+    memcpy(h->p_vaf, vp.data(), vp.size() * sizeof(double));
+    memcpy(h->p_desc, desc.data(), desc.size());
     h->cap = params->level_capacity > 0 ? params->level_capacity : (1ll << 21);
     if (h->cap < 1024) h->cap = 1024;
     h->chunk_max = std::min<long long>(h->cap, 1ll << 21);
     h->cand_cap = std::max<long long>(h->cap, 1ll << 23);
     h->b_level.assign(Lp, DevBuf{});
     h->head.assign(Lp, 0); h->tail.assign(Lp, 0);
-    {
-        // every level starts as a view of kNarrowCap items into one slab; a level that needs more gets
-        // its own buffer from the pool (ensure)
-        const size_t per = (size_t)kNarrowCap * h->stride;
-        CKE(ensure(h, h->b_slab, per * Lp));
-        for (int lv = 0; lv < Lp; lv++) {
-            h->b_level[lv].p = static_cast<char *>(h->b_slab.p) + per * lv;
-            h->b_level[lv].bytes = per;
-            h->b_level[lv].view = true;
-        }
-    }
     CKE(ensure(h, h->b_small, 256));
-    CKE(ensure(h, h->b_sched, sizeof(Sched)));
     h->h_meta = reinterpret_cast<TopMeta *>(h->h_scan + 1);
     h->h_sched = reinterpret_cast<Sched *>(h->h_meta + 1);
     h->h_rout = reinterpret_cast<ReplayOut *>(h->h_sched + 1);
     h->narrow = getenv("LICHEE_NO_NARROW") == nullptr;
-    for (int i = 0; i < 2; i++) {
-        CKE(ensure(h, h->b_top[i], sizeof(Cand) * LICHEE_MAX_SAVE));
-        CKE(ensure(h, h->b_tree[i], (size_t)LICHEE_MAX_SAVE * 2 * h->stride));
-    }
     h->net.vaf = reinterpret_cast<const double *>(nb);
     h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
     h->net.leaf_static = reinterpret_cast<const double *>(nb + o_ls);
@@ -3639,7 +3670,6 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
         }
     }
 #undef CKE
-    CKD(cudaStreamSynchronize(h->stream));
 #undef CKD
     *out = h;
     return LICHEE_OK;
@@ -3784,6 +3814,7 @@ int lichee_search_export_ranked(const lichee_search *h, void *dst, int device_pt
     if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
     if (h->ref_result) { set_err("export_ranked: the list is a reference-order result (one sequential search); shard with part_count > 1 or ref_order_budget < 0"); return LICHEE_ERR_STATE; }
     CK(cudaSetDevice(h->device));
+    if (upload_tables(const_cast<lichee_search *>(h)) != LICHEE_OK) return LICHEE_ERR_CUDA;
     const long long rb = 24 + h->stride;
     unsigned char *d = nullptr;
     lichee_search *hm = const_cast<lichee_search *>(h);
@@ -3808,6 +3839,7 @@ int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_
     if (!h->ran) { set_err("lichee_search_run has not completed"); return LICHEE_ERR_STATE; }
     if (h->ref_result) { set_err("merge_ranked: the list on this handle is a reference-order result"); return LICHEE_ERR_STATE; }
     CK(cudaSetDevice(h->device));
+    if (upload_tables(h) != LICHEE_OK) return LICHEE_ERR_CUDA;
     const long long rb = 24 + h->stride;
     const long long n = (long long)n_lists * h->prm.num_save;
     if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)n) != LICHEE_OK) return LICHEE_ERR_CUDA;
