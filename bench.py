@@ -369,9 +369,15 @@ def main():
             torch.cuda.synchronize()
             search.merge_ranked(gather_out.data_ptr(), world, device_ptr=True)
 
+    phase_ms = {"search": 0.0, "merge": 0.0}
+
     def step_resident():
+        t0 = time.perf_counter()
         st = resident.run()
+        t1 = time.perf_counter()
         merge(resident)
+        phase_ms["search"] += 1e3 * (t1 - t0)
+        phase_ms["merge"] += 1e3 * (time.perf_counter() - t1)
         return st
 
     def step_e2e():
@@ -386,6 +392,7 @@ def main():
         step_resident()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    phase_ms["search"] = phase_ms["merge"] = 0.0
     t0 = time.perf_counter()
     stats = [step_resident() for _ in range(args.steps)]
     barrier()
@@ -421,6 +428,15 @@ def main():
     checks_all, scored_all, launches_all, e2e_checks_all, eval_all, leaf_all, bounded_all = [float(x) for x in agg.tolist()]
     t_dev, t_e2e = [float(x) for x in tmax.tolist()]
 
+    per_rank = None
+    if world > 1:
+        # where each rank's step went: its own slice search (prologue included) and the export / all_gather / merge
+        mine = {"rank": rank, "search_ms_per_step": round(phase_ms["search"] / args.steps, 3),
+                "merge_ms_per_step": round(phase_ms["merge"] / args.steps, 3),
+                "device_ms_per_step": round(sum(s.kernel_ms_total for s in stats) / args.steps, 3),
+                "valid_trees_per_step": int(stats[-1].num_trees), "launches_per_step": int(stats[-1].num_launches)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     strong = None
     if world > 1 and not args.no_strong:
         strong = strong_scaling_leg(lichee_b200, torch, dist, rank, world, local, args)
@@ -483,6 +499,8 @@ def main():
                       "(it contains everything, host round trips and the merge included); device_ms_per_step and kernel_ms_per_step: "
                       "CUDA events on the library's own stream (rank 0)",
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if strong is not None:
             line["strong_scaling"] = strong
         if world == 1:

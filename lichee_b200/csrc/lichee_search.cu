@@ -922,7 +922,7 @@ template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
 check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, uint4 *__restrict__ mask_out,
               unsigned *__restrict__ count_out, uint4 *__restrict__ both_out, uint4 *__restrict__ masku_out,
-              unsigned *__restrict__ flag_out, const TopMeta *meta, int num_save, int run_len) {
+              unsigned *__restrict__ flag_out, double *__restrict__ bound_out, const TopMeta *meta, int num_save, int run_len) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
@@ -1035,11 +1035,13 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
                 }
             }
             unsigned flag = 0;
+            double tb = 0.0;
             if (prune) {
-                const double tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
+                tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
                 flag = tb > tmax ? 1u : 0u;
             }
             if (lane == 0) {
+                bound_out[it] = tb;                      // kept with the children: a later, tighter threshold re-tests it for free
                 mask_out[it] = make_uint4(bv[0], bv[1], bv[2], bv[3]);
                 count_out[it] = __popc(bv[0]) + __popc(bv[1]) + __popc(bv[2]) + __popc(bv[3]);
                 both_out[it] = make_uint4(bb[0], bb[1], bb[2], bb[3]);
@@ -1058,8 +1060,8 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
 __global__ void __launch_bounds__(kThreads)
 emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, const uint4 *__restrict__ mask,
              const unsigned *__restrict__ off, const uint4 *__restrict__ both, const uint4 *__restrict__ masku,
-             const unsigned *__restrict__ flag, unsigned *__restrict__ out, uint4 *__restrict__ lmask_out,
-             unsigned *__restrict__ lcnt_out, ScanOut *so) {
+             const unsigned *__restrict__ flag, const double *__restrict__ bound, unsigned *__restrict__ out,
+             uint4 *__restrict__ lmask_out, unsigned *__restrict__ lcnt_out, double *__restrict__ lbound_out, ScanOut *so) {
     __shared__ uint8_t cand_s[kMaxN], cidx2_s[kMaxN];
     __shared__ unsigned candq2_s[4];
     const int level = net.L - 2;
@@ -1107,6 +1109,7 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
             continue;
         }
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+        const double tb = bound[it];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             unsigned b = mw[g];
@@ -1123,6 +1126,7 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
                     const unsigned cnt = __popc(lm[0]) + __popc(lm[1]) + __popc(lm[2]) + __popc(lm[3]);
                     lmask_out[dst] = make_uint4(lm[0], lm[1], lm[2], lm[3]);
                     lcnt_out[dst] = cnt;
+                    lbound_out[dst] = tb;
                     my_trees += cnt;
                     my_live += 1;
                 }
@@ -1148,11 +1152,13 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
 template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__restrict__ fit, long long item_base,
-            const unsigned *__restrict__ lcnt, int part, TopMeta *meta,
-            int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len) {
+            const unsigned *__restrict__ lcnt, const double *__restrict__ lbound, int part, TopMeta *meta,
+            int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len_arg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
+    const bool adjacent_only = run_len_arg < 0;            // (experiment switch LICHEE_LEAF_ADJACENT: the round-1 rule)
+    const int run_len = run_len_arg < 0 ? -run_len_arg : run_len_arg;
     __shared__ double fstat_s[kMaxN];          // by row: E' of a candidate whose only child is the last node
     __shared__ uint8_t cidx_s[kMaxN];          // by row: candidate index (valid where candq has the bit)
     __shared__ unsigned candq_s[4], okq_s[4];  // rows that are candidates / that pass with no other child
@@ -1221,6 +1227,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     unsigned fstale[4] = {0, 0, 0, 0};
     bool hopeless = false;
     const bool prune = net.prune != 0 && full;
+    const bool prune_pre = prune && !adjacent_only;           // (LICHEE_LEAF_ADJACENT also switches the prefilter off: round-1 behaviour)
     const bool has_v = level >= 1;                          // a tree position L-2 exists
     const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     // The pass mask and the number of valid trees of every item were written by emit2_kernel together with
@@ -1239,7 +1246,11 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     const long long idx = blk + lane;
     const unsigned cw = idx < run1 ? __ldg(lcnt + idx) : kBounded;
     if (idx < run1) my_valid += cw & kCountMask;
-    unsigned live = __ballot_sync(kFull, (cw & kBounded) == 0);
+    // not flagged when the level above was checked -- but the threshold has tightened since (a burst earlier in
+    // this fill): the base's bound travelled with the item, so the re-test costs one load instead of an evaluation
+    bool is_live = (cw & kBounded) == 0;
+    if (is_live && prune_pre && __ldg(lbound + idx) > tmax) is_live = false;
+    unsigned live = __ballot_sync(kFull, is_live);
     {
         const int nblk = run1 - blk < 32 ? (int)(run1 - blk) : 32;
         my_bounded += nblk - __popc(live);
@@ -1260,7 +1271,10 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
         // base item: v unassigned
         const unsigned wb = (has_v && lane == wl2) ? (w | (0xffu << sh2)) : w;
         unsigned todo[4] = {0, 0, 0, 0};                     // base rows to (re)compute for this item
-        bool fresh = it != last_it + 1;                      // no state from the item just before this one
+        // The state belongs to the base of the item evaluated LAST by this warp, wherever that item was: the rows to
+        // redo come from the bytes in which the two bases differ, so bounded items in between (97 % of a level on
+        // the headline network) do not force a full evaluation of the next live one.
+        bool fresh = last_it < 0 || (adjacent_only && it != last_it + 1);
         last_it = it;
         if (!fresh) {
             const unsigned diff = wb ^ wb_prev;
@@ -1450,12 +1464,15 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
 
 // Gives every candidate its canonical sequence number (rank among the valid trees) now that the
 // scan has numbered the items, and retires the ones beyond Parameters.MAX_NUM_TREES.
+// Also writes the selection keys as two plain arrays (score bits, seq; ~0 for an empty slot): the radix passes
+// then read 8 or 16 bytes per candidate instead of the 32-byte record.
 __global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, const uint4 *__restrict__ mask,
-                                 const unsigned *__restrict__ off, long long seq_base, long long max_trees) {
+                                 const unsigned *__restrict__ off, long long seq_base, long long max_trees,
+                                 unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     Cand c = cands[t];
-    if (c.pad) return;
+    if (c.pad) { key0[t] = ~0ull; key1[t] = ~0ull; return; }
     const long long it = (long long)c.origin - item_base;
     const unsigned i = c.pstar >> 8;
     const uint4 m4 = mask[it];
@@ -1467,8 +1484,10 @@ __global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, 
     c.pstar &= 0xffu;
     if (seq >= max_trees) {
         c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu; c.pad = 1;
+        key0[t] = ~0ull; key1[t] = ~0ull;
     } else {
         c.seq = seq;
+        key0[t] = (unsigned long long)__double_as_longlong(c.score); key1[t] = (unsigned long long)seq;
     }
     cands[t] = c;
 }
@@ -1798,7 +1817,8 @@ __global__ void radix12_init(Radix12State *st, const TopMeta *meta, unsigned lon
 }
 
 __global__ void __launch_bounds__(256)
-radix12_pass(const Cand *__restrict__ cands, long long m, Radix12State *st, unsigned tile) {
+radix12_pass(const unsigned long long *__restrict__ key0, const unsigned long long *__restrict__ key1, long long m,
+             Radix12State *st, unsigned tile) {
     __shared__ unsigned h[4096];
     __shared__ unsigned part[256];
     __shared__ bool last;
@@ -1809,13 +1829,13 @@ radix12_pass(const Cand *__restrict__ cands, long long m, Radix12State *st, unsi
     for (int i = threadIdx.x; i < 4096; i += 256) h[i] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        const Cand c = cands[i];
-        if (c.pad) continue;
-        const unsigned long long k0 = (unsigned long long)__double_as_longlong(c.score), k1 = (unsigned long long)c.seq;
+        const unsigned long long k0 = key0[i];
+        if (k0 == ~0ull) continue;                       // empty slot
         if (word == 0) {
             if (hi >= 64 || (k0 >> hi) == (p0 >> hi)) atomicAdd(&h[(unsigned)(k0 >> shift) & dmask], 1u);
-        } else if (k0 == p0 && (hi >= 64 || (k1 >> hi) == (p1 >> hi))) {
-            atomicAdd(&h[(unsigned)(k1 >> shift) & dmask], 1u);
+        } else if (k0 == p0) {
+            const unsigned long long k1 = key1[i];
+            if (hi >= 64 || (k1 >> hi) == (p1 >> hi)) atomicAdd(&h[(unsigned)(k1 >> shift) & dmask], 1u);
         }
     }
     __syncthreads();
@@ -1865,16 +1885,16 @@ radix12_pass(const Cand *__restrict__ cands, long long m, Radix12State *st, unsi
 }
 
 __global__ void __launch_bounds__(256)
-radix12_compact(const Cand *__restrict__ cands, long long m, Radix12State *st, Cand *__restrict__ out, long long out_cap) {
+radix12_compact(const Cand *__restrict__ cands, const unsigned long long *__restrict__ key0,
+                const unsigned long long *__restrict__ key1, long long m, Radix12State *st, Cand *__restrict__ out, long long out_cap) {
     if (!st->done) return;
     const unsigned long long t0 = st->thresh[0], t1 = st->thresh[1];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        const Cand c = cands[i];
-        if (c.pad) continue;
-        const unsigned long long k0 = (unsigned long long)__double_as_longlong(c.score), k1 = (unsigned long long)c.seq;
-        if (k0 < t0 || (k0 == t0 && k1 <= t1)) {
+        const unsigned long long k0 = key0[i];
+        if (k0 == ~0ull) continue;
+        if (k0 < t0 || (k0 == t0 && key1[i] <= t1)) {
             const unsigned long long slot = atomicAdd(&st->kept, 1ull);
-            if ((long long)slot < out_cap) out[slot] = c;
+            if ((long long)slot < out_cap) out[slot] = cands[i];       // only the survivors' records are read
         }
     }
 }
@@ -2539,9 +2559,9 @@ struct lichee_search {
     std::vector<long long> head, tail;
     long long cap = 0;                       // upper bound on items per level buffer
     long long cand_cap = 0;                  // upper bound on candidates one last-level launch may append
-    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_radix12, b_cands[2], b_top[2], b_tree[2];
-    DevBuf b_mask2, b_mask3, b_flag;         // level L-2 chunks: "v and u" mask, "u without v" mask, bounded flag
-    DevBuf b_lmask, b_lcnt;                  // last level, parallel to its item buffer: pass mask, count | flags
+    DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_radix12, b_key0, b_key1, b_cands[2], b_top[2], b_tree[2];
+    DevBuf b_mask2, b_mask3, b_flag, b_bound; // level L-2 chunks: "v and u" mask, "u without v" mask, bounded flag, bound value
+    DevBuf b_lmask, b_lcnt, b_lbound;        // last level, parallel to its item buffer: pass mask, count | flags, bound of the base
     uint4 sok_last{};                        // static pass mask of the last node (n == 2: the only item's mask)
     DevBuf b_slab;                           // kNarrowCap items for every level (what the narrow scheduler emits into)
     DevBuf b_sched;                          // Sched, device copy
@@ -2727,8 +2747,9 @@ int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq
     h->stats.kernel_launches[LICHEE_K_SELECT]++;
     struct { unsigned long long kept; int shift; unsigned done; } rd{};
     for (int round = 0; round < 2; round++) {           // 6 + 6 digits cover the 128 key bits; finished passes return at once
-        for (int p = 0; p < 6; p++) radix12_pass<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, (unsigned)kSelTile);
-        radix12_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), m, st, h->d_cands(1), (long long)kSelTile);
+        const unsigned long long *k0 = static_cast<const unsigned long long *>(h->b_key0.p), *k1 = static_cast<const unsigned long long *>(h->b_key1.p);
+        for (int p = 0; p < 6; p++) radix12_pass<<<grid, 256, 0, h->stream>>>(k0, k1, m, st, (unsigned)kSelTile);
+        radix12_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), k0, k1, m, st, h->d_cands(1), (long long)kSelTile);
         CK(cudaGetLastError());
         h->stats.num_launches += 7;
         h->stats.kernel_launches[LICHEE_K_SELECT] += 7;
@@ -2842,7 +2863,8 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     h->tail[0] = 1;
     if (L == 1) {
         // two nodes: the only item is the empty one, its pass mask is the static mask of the last node
-        if (ensure(h, h->b_lmask, sizeof(uint4)) != LICHEE_OK || ensure(h, h->b_lcnt, 4) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        if (ensure(h, h->b_lmask, sizeof(uint4)) != LICHEE_OK || ensure(h, h->b_lcnt, 4) != LICHEE_OK || ensure(h, h->b_lbound, 8) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        CK(cudaMemsetAsync(h->b_lbound.p, 0, 8, h->stream));
         const uint4 m = h->sok_last;
         const unsigned c = (unsigned)(__builtin_popcount(m.x) + __builtin_popcount(m.y) + __builtin_popcount(m.z) + __builtin_popcount(m.w));
         CK(cudaMemcpyAsync(h->b_lmask.p, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
@@ -2960,7 +2982,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             fill_trees = (long long)h->h_scan->trees;
             // emit2's algorithmic bytes: masks, flag and offset of every parent, a count word per child, and
             // item + mask for the children that are not bounded
-            st.kernel_bytes[LICHEE_K_EMIT] += fill_parents * 56ll + fill_items * 4ll + fill_live * (long long)(h->stride + 16);
+            st.kernel_bytes[LICHEE_K_EMIT] += fill_parents * 64ll + fill_items * 4ll + fill_live * (long long)(h->stride + 24);
         }
         if (leaf && fill_items > 0 && fill_live == 0 && B == pending && pending == fill_items) {
             // no item of this fill can reach the ranked list: its trees are counted, nothing is launched
@@ -2989,7 +3011,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
         const bool dual = lv == L - 2;                       // the level whose children are the last-level items
         if (dual && (ensure(h, h->b_mask2, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_mask3, sizeof(uint4) * (size_t)B) != LICHEE_OK ||
-                     ensure(h, h->b_flag, 4 * (size_t)B) != LICHEE_OK))
+                     ensure(h, h->b_flag, 4 * (size_t)B) != LICHEE_OK || ensure(h, h->b_bound, 8 * (size_t)B) != LICHEE_OK))
             return LICHEE_ERR_CUDA;
         if (ensure(h, h->b_mask, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_cnt, 4 * (size_t)B) != LICHEE_OK ||
             ensure(h, h->b_off, 4 * (size_t)B) != LICHEE_OK ||
@@ -3010,10 +3032,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             const int grid = (int)std::min<long long>(148 * 2, (B + (long long)run_len * kWarpsPerBlock - 1) / ((long long)run_len * kWarpsPerBlock));
             check2_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(
                 h->net, items, B, h->d_mask(), h->d_cnt(), static_cast<uint4 *>(h->b_mask2.p), static_cast<uint4 *>(h->b_mask3.p),
-                static_cast<unsigned *>(h->b_flag.p), h->d_meta(), h->prm.num_save, run_len);
+                static_cast<unsigned *>(h->b_flag.p), static_cast<double *>(h->b_bound.p), h->d_meta(), h->prm.num_save, run_len);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_CHECK]++;
-            st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 56);
+            st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 64);
         } else if (!leaf) {
             if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_launches[LICHEE_K_CHECK]++;
@@ -3034,11 +3056,12 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             int grid = grid_for(B);
             // runs of items are claimed dynamically by the warps, in 32-item blocks (a bounded item costs a
             // few instructions, an evaluated one hundreds)
-            int run_len = (int)std::min<long long>(256, std::max<long long>(32, (B / ((long long)grid * kWarpsPerBlock * 4) + 31) / 32 * 32));
+            int run_len = 32;    // (measured: runs of 256 items left a tail of ~1 ms per step; a run of bounded items costs a few instructions)
             if (const char *e = getenv("LICHEE_LEAF_GRID")) grid = std::min(grid, atoi(e));
             if (const char *e = getenv("LICHEE_LEAF_RUN")) run_len = std::min(run_len, std::max(32, atoi(e)));
+            if (getenv("LICHEE_LEAF_ADJACENT")) run_len = -run_len;
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
-                h->net, items, h->d_scan(), h->head[lv], lcnt, R, h->d_meta(), h->prm.num_save,
+                h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], R, h->d_meta(), h->prm.num_save,
                 h->d_cands(0), cand_cap, run_len);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_LEAF]++;
@@ -3079,8 +3102,11 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             }
             if (m > 0) {
+                if (ensure(h, h->b_key0, 8 * (size_t)m) != LICHEE_OK || ensure(h, h->b_key1, 8 * (size_t)m) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], lmask,
-                                                                             h->d_off(), seq_base, h->prm.max_num_trees);
+                                                                             h->d_off(), seq_base, h->prm.max_num_trees,
+                                                                             static_cast<unsigned long long *>(h->b_key0.p),
+                                                                             static_cast<unsigned long long *>(h->b_key1.p));
                 CK(cudaGetLastError());
                 st.num_launches++;
                 int src = 0;
@@ -3117,13 +3143,15 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             if (total_fit > 0) {
                 if (ensure(h, h->b_level[lv + 1], (size_t)total_fit * h->stride) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 if (dual) {
-                    if (ensure(h, h->b_lmask, sizeof(uint4) * (size_t)total_fit) != LICHEE_OK || ensure(h, h->b_lcnt, 4 * (size_t)total_fit) != LICHEE_OK)
+                    if (ensure(h, h->b_lmask, sizeof(uint4) * (size_t)total_fit) != LICHEE_OK || ensure(h, h->b_lcnt, 4 * (size_t)total_fit) != LICHEE_OK ||
+                        ensure(h, h->b_lbound, 8 * (size_t)total_fit) != LICHEE_OK)
                         return LICHEE_ERR_CUDA;
                     CK(cudaMemsetAsync(&h->d_scan()->live, 0, 2 * sizeof(unsigned long long), h->stream));
                     emit2_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(
                         h->net, items, n_fit, h->d_mask(), h->d_off(), static_cast<const uint4 *>(h->b_mask2.p),
-                        static_cast<const uint4 *>(h->b_mask3.p), static_cast<const unsigned *>(h->b_flag.p), h->level(lv + 1),
-                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p), h->d_scan());
+                        static_cast<const uint4 *>(h->b_mask3.p), static_cast<const unsigned *>(h->b_flag.p),
+                        static_cast<const double *>(h->b_bound.p), h->level(lv + 1),
+                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p), static_cast<double *>(h->b_lbound.p), h->d_scan());
                     CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
                     fill_pending = true;                      // read at the next last-level chunk
                     fill_items = total_fit;
@@ -3368,11 +3396,11 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_mask); give_back(h, h->b_cnt); give_back(h, h->b_off); give_back(h, h->b_tile);
     give_back(h, h->b_small);
     give_back(h, h->b_radix);
-    give_back(h, h->b_radix12);
+    give_back(h, h->b_radix12); give_back(h, h->b_key0); give_back(h, h->b_key1);
     give_back(h, h->b_slab);
     give_back(h, h->b_sched);
-    give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag);
-    give_back(h, h->b_lmask); give_back(h, h->b_lcnt);
+    give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag); give_back(h, h->b_bound);
+    give_back(h, h->b_lmask); give_back(h, h->b_lcnt); give_back(h, h->b_lbound);
     give_back(h, h->b_rblob); give_back(h, h->b_rrec);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     {
