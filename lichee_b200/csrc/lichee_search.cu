@@ -362,19 +362,36 @@ constexpr unsigned kBounded = 0x40000000u;     // no tree below this item can en
 __device__ __forceinline__ unsigned scan_value(unsigned x, int live_only) {
     return (live_only && (x & kBounded)) ? 0u : x & kCountMask;
 }
+// Live mode with the stored bounds (last level): an item whose base's bound exceeds what the CURRENT threshold
+// admits yields no candidate either -- the same test leaf_kernel applies before it touches the item -- so the chunk
+// extends over everything a burst earlier in the fill has made hopeless.
+__device__ __forceinline__ double admit_bound(const TopMeta *meta, int num_save, bool &full, double &tau);
+__device__ __forceinline__ double live_tmax(int live_only, const double *lb, const TopMeta *meta, int num_save) {
+    if (!live_only || !lb) return INFINITY;
+    bool full;
+    double tau;
+    return admit_bound(meta, num_save, full, tau);
+}
+__device__ __forceinline__ unsigned scan_value(unsigned x, int live_only, const double *lb, long long idx, double tmax) {
+    if (!live_only) return x & kCountMask;
+    if (x & kBounded) return 0u;
+    if (lb && __ldg(lb + idx) > tmax) return 0u;
+    return x & kCountMask;
+}
 constexpr int kScanThreads = 256;
 constexpr int kScanPer = 8;
 constexpr int kScanTile = kScanThreads * kScanPer;
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_tiles(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned long long *tile_sum,
-           long long n, int live_only) {
+           long long n, int live_only, const double *__restrict__ lb, const TopMeta *meta, int num_save) {
     __shared__ unsigned warp_tot[kScanThreads / 32];
+    const double tmax = live_tmax(live_only, lb, meta, num_save);
     const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanPer;
     unsigned v[kScanPer], run = 0;
 #pragma unroll
     for (int i = 0; i < kScanPer; i++) {
-        v[i] = base + i < n ? scan_value(in[base + i], live_only) : 0;
+        v[i] = base + i < n ? scan_value(in[base + i], live_only, lb, base + i, tmax) : 0;
         run += v[i];
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -423,7 +440,8 @@ __global__ void scan_tile_sums(unsigned long long *tile_sum, int n_tiles, ScanOu
 __global__ void __launch_bounds__(kScanThreads)
 scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
             const unsigned long long *__restrict__ tile_sum, long long n, unsigned long long limit,
-            ScanOut *out, int live_only) {
+            ScanOut *out, int live_only, const double *__restrict__ lb, const TopMeta *meta, int num_save) {
+    const double tmax = live_tmax(live_only, lb, meta, num_save);
     const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanPer;
     const unsigned long long add = tile_sum[blockIdx.x];
     unsigned long long best = 0;
@@ -433,7 +451,7 @@ scan_finish(const unsigned *__restrict__ cnt, unsigned *__restrict__ off,
         if (idx < n) {
             const unsigned long long ex = add + off[idx];
             off[idx] = (unsigned)ex;
-            const unsigned long long inc = ex + scan_value(cnt[idx], live_only);
+            const unsigned long long inc = ex + scan_value(cnt[idx], live_only, lb, idx, tmax);
             if (inc <= limit) best = ((unsigned long long)(idx + 1) << 32) | inc;
         }
     }
@@ -459,7 +477,8 @@ constexpr long long kScanSingleMax = 4096;
 
 __global__ void __launch_bounds__(kScanSingleThreads)
 scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long long n, unsigned long long limit,
-            ScanOut *out, int live_only) {
+            ScanOut *out, int live_only, const double *__restrict__ lb, const TopMeta *meta, int num_save) {
+    const double tmax = live_tmax(live_only, lb, meta, num_save);
     __shared__ unsigned warp_tot[kScanSingleThreads / 32];
     __shared__ unsigned long long best_s;
     if (threadIdx.x == 0) best_s = 0;
@@ -467,7 +486,7 @@ scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long l
     const long long lo = (long long)threadIdx.x * per;
     const long long hi = lo + per < n ? lo + per : n;
     unsigned run = 0;
-    for (long long i = lo; i < hi; i++) run += scan_value(cnt[i], live_only);
+    for (long long i = lo; i < hi; i++) run += scan_value(cnt[i], live_only, lb, i, tmax);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned inc = run;
 #pragma unroll
@@ -485,7 +504,7 @@ scan_single(const unsigned *__restrict__ cnt, unsigned *__restrict__ off, long l
     unsigned long long ex = woff + inc - run, best = 0;
     for (long long i = lo; i < hi; i++) {
         off[i] = (unsigned)ex;
-        ex += scan_value(cnt[i], live_only);
+        ex += scan_value(cnt[i], live_only, lb, i, tmax);
         if (ex <= limit) best = ((unsigned long long)(i + 1) << 32) | ex;
     }
     if (best) atomicMax(&best_s, best);
@@ -2643,16 +2662,19 @@ int launch_check(lichee_search *h, int lv, const unsigned *items, long long n_it
     return LICHEE_OK;
 }
 
-int launch_scan(lichee_search *h, const unsigned *cnt, long long n_items, unsigned long long limit, int live_only = 0) {
+int launch_scan(lichee_search *h, const unsigned *cnt, long long n_items, unsigned long long limit, int live_only = 0,
+                const double *lb = nullptr) {
     if (n_items <= kScanSingleMax) {
-        scan_single<<<1, kScanSingleThreads, 0, h->stream>>>(cnt, h->d_off(), n_items, limit, h->d_scan(), live_only);
+        scan_single<<<1, kScanSingleThreads, 0, h->stream>>>(cnt, h->d_off(), n_items, limit, h->d_scan(), live_only, lb, h->d_meta(),
+                                                           h->prm.num_save);
         h->stats.num_launches += 1;
         h->stats.kernel_launches[LICHEE_K_SCAN] += 1;
     } else {
         const int tiles = (int)((n_items + kScanTile - 1) / kScanTile);
-        scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(cnt, h->d_off(), h->d_tile(), n_items, live_only);
+        scan_tiles<<<tiles, kScanThreads, 0, h->stream>>>(cnt, h->d_off(), h->d_tile(), n_items, live_only, lb, h->d_meta(), h->prm.num_save);
         scan_tile_sums<<<1, 32, 0, h->stream>>>(h->d_tile(), tiles, h->d_scan());
-        scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(cnt, h->d_off(), h->d_tile(), n_items, limit, h->d_scan(), live_only);
+        scan_finish<<<tiles, kScanThreads, 0, h->stream>>>(cnt, h->d_off(), h->d_tile(), n_items, limit, h->d_scan(), live_only, lb,
+                                                          h->d_meta(), h->prm.num_save);
         h->stats.num_launches += 3;
         h->stats.kernel_launches[LICHEE_K_SCAN] += 3;
     }
@@ -3051,7 +3073,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             //  yet large enough for a whole search under the reference's MAX_NUM_TREES = 100000)
             long long cand_limit = std::max<long long>(128, (cand_cap - (long long)kCandBatch * 148 * 3 * kWarpsPerBlock) / 5 * 4);
             if (!list_full) cand_limit = std::min<long long>(cand_limit, 1 << 17);
-            if (launch_scan(h, lcnt, B, (unsigned long long)cand_limit, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            if (const char *e = getenv("LICHEE_CAND_LIMIT")) cand_limit = std::min<long long>(cand_limit, atoll(e));
+            const double *lb_chunk = h->net.prune && !getenv("LICHEE_LEAF_ADJACENT") ? static_cast<const double *>(h->b_lbound.p) + h->head[lv] : nullptr;
+            if (launch_scan(h, lcnt, B, (unsigned long long)cand_limit, 1, lb_chunk) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             int grid = grid_for(B);
             // runs of items are claimed dynamically by the warps, in 32-item blocks (a bounded item costs a
