@@ -33,7 +33,7 @@ def host_replay(lib, adj, vaf, margin, max_trees=100000, max_grow=10**8, cap=100
     off, idx = oracle.to_csr(adj)
     orders = np.zeros((cap, n), dtype=np.int32)
     parents = np.zeros((cap, n), dtype=np.int32)
-    stats = np.zeros(5, dtype=np.int64)
+    stats = np.zeros(8, dtype=np.int64)
     P = ctypes.c_void_p
     lib.replay_host_search(ctypes.c_int(n), ctypes.c_int(S), P(off.ctypes.data), P(idx.ctypes.data), P(vaf.ctypes.data),
                            ctypes.c_double(margin), ctypes.c_longlong(max_trees), ctypes.c_longlong(max_grow),
