@@ -106,6 +106,32 @@ class ClockSampler:
         return out
 
 
+def ncu_note():
+    """Issue-slot and occupancy figures of the hot kernels from the committed ncu summaries (profiles/r02_*_ncu_full.csv,
+    `ncu --set full` of the same binary): what binds the kernels when it is not HBM."""
+    import csv
+    def pick(name, metric, col=-2):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            return None
+        for r in csv.reader(open(path)):
+            if r and r[0] == metric:
+                return r[1:-1]
+        return None
+    parts = []
+    for label, f in (("leaf_kernel (an all-dismissed chunk / an ordinary chunk / a burst)", "r02_leaf_kernel_ncu_full.csv"),
+                     ("check2_kernel", "r02_check2_kernel_ncu_full.csv"), ("replay_kernel (one warp)", "r02_replay_kernel_ncu_full.csv")):
+        iss = pick(f, "smsp__issue_active.avg.pct_of_peak_sustained_active")
+        wrp = pick(f, "sm__warps_active.avg.pct_of_peak_sustained_active")
+        drm = pick(f, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+        if iss and wrp and drm:
+            parts.append(f"{label}: issue slots active {'/'.join(f'{float(x):.0f}' for x in iss)} %, warps active "
+                         f"{'/'.join(f'{float(x):.0f}' for x in wrp)} %, DRAM {'/'.join(f'{float(x):.1f}' for x in drm)} % of peak")
+    return ("integer/byte frontier work: the kernels are bound by instruction issue and dependent-instruction latency, not by HBM "
+            "(ncu --set full, profiles/r02_*_ncu_full.csv): " + "; ".join(parts) + ". DRAM bytes of a launch = its algorithmic bytes; "
+            "`traffic` is the DRAM byte count of ONE captured burst launch (profiles/traffic.json).")
+
+
 def bundled_search_times(lichee_b200, with_cpu):
     """-build search wall time on the bundled ccRCC / HGSC networks (BASELINE configs[0..2], README
     settings, committed fixtures): end to end through the public API from host arrays, median of 5, in the
@@ -488,10 +514,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "launches": nl[dom], "avg_launch_ms": ms[dom] / max(nl[dom], 1),
                          "algorithmic_bytes_per_launch": by[dom] / max(nl[dom], 1),
-                         "note": "integer/byte frontier work: the kernels are bound by instruction issue and dependent-instruction latency, not by HBM "
-                                 "(ncu, final binary: check2_kernel 72% issue slots active, leaf_kernel 32-47% with 16-26% warps active because "
-                                 "only the unbounded items of a chunk are evaluated; DRAM 1-3% of peak, DRAM bytes = algorithmic bytes); "
-                                 "traffic is the DRAM byte count of ONE captured launch inside a good region, see profiles/README.md"},
+                         "note": ncu_note()},
             "kernel_ms_per_step": {K[i]: ms[i] / args.steps for i in range(5)},
             "kernel_launches_per_step": {K[i]: nl[i] / args.steps for i in range(5)},
             "device_ms_per_step": sum(s.kernel_ms_total for s in stats) / args.steps,
