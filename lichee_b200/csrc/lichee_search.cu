@@ -1637,6 +1637,29 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         }
         __syncthreads();
         res = out;
+    } else if (external_records == 2) {
+        // Merge of ranked lists (one per GPU): every list arrives SORTED, `num_save` entries each.  The held tile is
+        // ascending; a list loaded in reverse behind it makes the 2048 entries bitonic, so the eleven compare-exchange
+        // steps of a bitonic MERGE order them -- not the 66 steps of a full sort per list.
+        for (unsigned long long base = 0; base < m; base += (unsigned)num_save) {
+            for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
+                e[2 * kSelTile - 1 - t] = (t < num_save && base + t < m) ? cands[base + t] : sentinel;
+            __syncthreads();
+            for (int j = kSelTile; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < 2 * kSelTile; t += kSelThreads) {
+                    const int x = t ^ j;
+                    if (x > t) {
+                        const Cand a = e[t], b = e[x];
+                        if (cand_less(b, a)) { e[t] = b; e[x] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        unsigned mine = 0;
+        for (int t = threadIdx.x; t < kSelTile; t += kSelThreads) mine += e[t].pad == 0;
+        if (mine) atomicAdd(&real_n, mine);
+        __syncthreads();
     } else {
         for (unsigned long long base = 0; base < m; base += kSelTile) {
             for (int t = threadIdx.x; t < kSelTile; t += kSelThreads)
@@ -3904,7 +3927,8 @@ int lichee_search_merge_ranked(lichee_search *h, const void *records, int32_t n_
     }
     records_to_cands<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(d, rb, n, h->d_cands(0), h->d_meta());
     CK(cudaGetLastError());
-    if (run_select(h, h->d_cands(0), n, nullptr, 1, d, rb) != LICHEE_OK) { if (tmp) cudaFree(tmp); return LICHEE_ERR_CUDA; }
+    // (every list is sorted: the merge form of the selection, unless the lists fit one rank-merge tile anyway)
+    if (run_select(h, h->d_cands(0), n, nullptr, n > kSelTile ? 2 : 1, d, rb) != LICHEE_OK) { if (tmp) cudaFree(tmp); return LICHEE_ERR_CUDA; }
     const int rc = fetch_top(h);
     if (tmp) cudaFree(tmp);
     return rc;

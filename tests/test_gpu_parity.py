@@ -194,6 +194,27 @@ def test_sharded_search_merges_to_the_single_gpu_answer(built):
             p.close()
 
 
+def test_merge_of_long_sorted_lists(built):
+    """More than one rank-merge tile of records (3 GPUs x 700 trees): the merge form of the selection (each list
+    arrives sorted; bitonic merge per list) must give the single-search list, ties included."""
+    import lichee_b200
+    e = [x for x in _networks() if x["dataset"] == "ccRCC/RK26.txt" and x["complete_edges"] and x["clustering"] == "single"][0]
+    for adj, vaf, margin in ((e["adj"], np.array(e["aaf"]), e["vaf_error_margin"]),) + tuple(
+            (n.adj, np.array(n.aaf), p.vaf_error_margin) for n, p in (make_instance(11, 5, seed=4),)):
+        whole, trees, _ = gpu_search(adj, vaf, margin, 700, max_num_trees=10**9)
+        P = 3
+        parts = [lichee_b200.LineageSearch(adj, vaf, margin, num_save=700, max_num_trees=10**9, part_rank=r, part_count=P)
+                 for r in range(P)]
+        for q in parts:
+            q.run()
+        recs = np.concatenate([q.export_ranked() for q in parts])
+        parts[1].merge_ranked(recs, P)
+        merged = parts[1].trees()
+        assert [(t.errorScore, t.parent) for t in merged] == [(t.errorScore, t.parent) for t in trees]
+        for q in parts:
+            q.close()
+
+
 def _networks():
     import json, os
     return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "networks_bundled.json")))
