@@ -592,6 +592,11 @@ std::vector<PHYTree> PHYNetwork::getLineageTrees(int numSave, lichee_search_stat
     lichee_default_params(&prmc);
     prmc.vaf_error_margin = prm.VAF_ERROR_MARGIN;
     prmc.num_save = std::max(1, numSave);
+    if (prmc.num_save > LICHEE_MAX_SAVE) {                 // the library ranks at most LICHEE_MAX_SAVE trees on the device
+        std::cerr << "lichee_b200: -s " << numSave << " exceeds " << LICHEE_MAX_SAVE << "; the first " << LICHEE_MAX_SAVE
+                  << " trees of the ranked list are saved\n";
+        prmc.num_save = LICHEE_MAX_SAVE;
+    }
     prmc.max_num_trees = prm.MAX_NUM_TREES;
     prmc.max_num_grow_calls = prm.MAX_NUM_GROW_CALLS;
     prmc.device = device;
