@@ -1176,7 +1176,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
-    const bool adjacent_only = run_len_arg < 0;            // (experiment switch LICHEE_LEAF_ADJACENT: the round-1 rule)
+    const bool adjacent_only = run_len_arg < 0;            // LICHEE_NO_PREFILTER=1: the round-1 rules (tests: nothing may move)
     const int run_len = run_len_arg < 0 ? -run_len_arg : run_len_arg;
     __shared__ double fstat_s[kMaxN];          // by row: E' of a candidate whose only child is the last node
     __shared__ uint8_t cidx_s[kMaxN];          // by row: candidate index (valid where candq has the bit)
@@ -1246,7 +1246,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     unsigned fstale[4] = {0, 0, 0, 0};
     bool hopeless = false;
     const bool prune = net.prune != 0 && full;
-    const bool prune_pre = prune && !adjacent_only;           // (LICHEE_LEAF_ADJACENT also switches the prefilter off: round-1 behaviour)
+    const bool prune_pre = prune && !adjacent_only;
     const bool has_v = level >= 1;                          // a tree position L-2 exists
     const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     // The pass mask and the number of valid trees of every item were written by emit2_kernel together with
@@ -2611,6 +2611,7 @@ struct lichee_search {
     TopMeta *h_meta = nullptr;               // pinned
     Sched *h_sched = nullptr;                // pinned
     bool narrow = true;                      // device-side scheduling of narrow chunks (LICHEE_NO_NARROW=1 turns it off)
+    bool no_prefilter = false;               // LICHEE_NO_PREFILTER=1: stored bounds not consulted by the last level and its scan
     int flip = 0;
     long long chunk_max = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -3096,17 +3097,14 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             //  yet large enough for a whole search under the reference's MAX_NUM_TREES = 100000)
             long long cand_limit = std::max<long long>(128, (cand_cap - (long long)kCandBatch * 148 * 3 * kWarpsPerBlock) / 5 * 4);
             if (!list_full) cand_limit = std::min<long long>(cand_limit, 1 << 17);
-            if (const char *e = getenv("LICHEE_CAND_LIMIT")) cand_limit = std::min<long long>(cand_limit, atoll(e));
-            const double *lb_chunk = h->net.prune && !getenv("LICHEE_LEAF_ADJACENT") ? static_cast<const double *>(h->b_lbound.p) + h->head[lv] : nullptr;
+            const double *lb_chunk = h->net.prune && !h->no_prefilter ? static_cast<const double *>(h->b_lbound.p) + h->head[lv] : nullptr;
             if (launch_scan(h, lcnt, B, (unsigned long long)cand_limit, 1, lb_chunk) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
-            int grid = grid_for(B);
+            const int grid = grid_for(B);
             // runs of items are claimed dynamically by the warps, in 32-item blocks (a bounded item costs a
             // few instructions, an evaluated one hundreds)
             int run_len = 32;    // (measured: runs of 256 items left a tail of ~1 ms per step; a run of bounded items costs a few instructions)
-            if (const char *e = getenv("LICHEE_LEAF_GRID")) grid = std::min(grid, atoi(e));
-            if (const char *e = getenv("LICHEE_LEAF_RUN")) run_len = std::min(run_len, std::max(32, atoi(e)));
-            if (getenv("LICHEE_LEAF_ADJACENT")) run_len = -run_len;
+            if (h->no_prefilter) run_len = -run_len;
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], R, h->d_meta(), h->prm.num_save,
                 h->d_cands(0), cand_cap, run_len);
@@ -3676,6 +3674,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->h_sched = reinterpret_cast<Sched *>(h->h_meta + 1);
     h->h_rout = reinterpret_cast<ReplayOut *>(h->h_sched + 1);
     h->narrow = getenv("LICHEE_NO_NARROW") == nullptr;
+    h->no_prefilter = getenv("LICHEE_NO_PREFILTER") != nullptr;
     h->net.vaf = reinterpret_cast<const double *>(nb);
     h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
     h->net.leaf_static = reinterpret_cast<const double *>(nb + o_ls);
