@@ -68,7 +68,9 @@ typedef struct lichee_search lichee_search;   /* opaque handle: one constraint n
  *   vaf_error_margin    -e                     Parameters.VAF_ERROR_MARGIN      (default 0.1)
  *   num_save            -s                     LineageEngine.Args.numSave       (default 1)
  *   max_num_trees       Parameters.MAX_NUM_TREES        (default 100000)
- *   max_num_grow_calls  Parameters.MAX_NUM_GROW_CALLS   (default 100000000)
+ *   max_num_grow_calls  Parameters.MAX_NUM_GROW_CALLS   (default 100000000).  Reference-order mode: the reference's own
+ *                       counter and early return (PHYNetwork.java:490), exactly.  Canonical mode: a WORK BUDGET -- accepted
+ *                       partial trees of a different traversal, checked at chunk boundaries; it cannot mean what :490 means.
  * -minRobustNodeSupport acts before this boundary (it decides which clusters are robust, hence
  * which nodes PHYNetwork.fixNetwork removes between two searches); the host re-submits the
  * adjusted network, see INTEGRATION.md.
@@ -93,8 +95,11 @@ typedef struct lichee_search_params {
 
 typedef struct lichee_search_stats {
     int64_t num_trees;           /* valid spanning trees found ("Found N valid tree(s)")        */
-    int64_t num_grow_calls;      /* accepted partial trees + 1, the reference's numGrowCalls    */
-    int64_t num_checks;          /* checkConstraint evaluations (candidate trees checked)       */
+    int64_t num_grow_calls;      /* reference-order mode: the reference's numGrowCalls, exactly; canonical mode:
+                                    accepted partial trees + 1 (what numGrowCalls would be for that traversal) */
+    int64_t num_checks;          /* reference-order mode: checkConstraint calls, exactly; canonical mode: sum-rule
+                                    DECISIONS (one per candidate extension; most are carried over, static or
+                                    belong to dismissed items -- see num_evaluated)                 */
     int64_t num_scored;          /* complete valid trees ranked: scored, or excluded from the
                                     ranked list by the lower bound of their partial tree        */
     int64_t num_launches;        /* kernels launched by lichee_search_run                       */
