@@ -117,8 +117,6 @@ typedef struct lichee_search_stats {
                                     base; reference order: every recorded tree)                   */
     int64_t num_bounded_items;   /* last-level frontier items skipped by the lower bound         */
     int64_t num_leaf_items;      /* last-level frontier items in total                           */
-    int64_t num_sampled_chunks;  /* last-level chunks scored behind a sampled threshold           */
-    int64_t num_probe_repeats;   /* ... of which had to be repeated without it (too few candidates) */
 } lichee_search_stats;
 
 void lichee_default_params(lichee_search_params *p);

@@ -52,8 +52,7 @@ class SearchStats(ctypes.Structure):
                 ("kernel_ms_total", ctypes.c_double), ("kernel_ms", ctypes.c_double * 5),
                 ("kernel_launches", ctypes.c_int64 * 5), ("kernel_bytes", ctypes.c_int64 * 5),
                 ("status", ctypes.c_uint32), ("num_saved", ctypes.c_uint32),
-                ("num_evaluated", ctypes.c_int64), ("num_bounded_items", ctypes.c_int64), ("num_leaf_items", ctypes.c_int64),
-                ("num_sampled_chunks", ctypes.c_int64), ("num_probe_repeats", ctypes.c_int64)]
+                ("num_evaluated", ctypes.c_int64), ("num_bounded_items", ctypes.c_int64), ("num_leaf_items", ctypes.c_int64)]
 
     KERNELS = ("check", "scan", "emit", "leaf", "select")
 

@@ -53,9 +53,6 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxN = LICHEE_MAX_NODES;
 constexpr int kMaxIncremental = 12;                // more changed parent rows than this: recompute the item
 constexpr int kCandBatch = 256;                    // candidate slots a warp reserves at a time
-constexpr unsigned kSampleMinTrees = 1u << 19;      // a chunk with fewer live trees cannot burst: not sampled
-constexpr int kSampleStride = 16;                  // one item in 16 is scored ahead of the chunk
-constexpr int kSampleRank = 256;                   // the threshold is the 256-th best sampled score (expected 4096 candidates)
 constexpr int kSelThreads = 1024;
 constexpr int kSelTile = 1024;
 constexpr unsigned kFull = 0xffffffffu;
@@ -121,8 +118,6 @@ struct TopMeta {             // device-resident state of the ranked list
     unsigned long long n_bounded; // items of the current leaf launch whose trees were excluded by the lower bound
     unsigned long long n_eval;   // trees of the current leaf launch whose total was computed
     unsigned long long kmin, kmax; // smallest / largest score bits among the candidates of the current leaf launch
-    unsigned long long probe_bits; // sampled threshold of the current chunk (score bits; ~0 = none): see sample_finish
-    unsigned long long n_real;     // candidate records (not padding) appended by the current leaf launch
 };
 
 struct ScanOut {             // written by the scan, read back by the host once per chunk
@@ -364,6 +359,9 @@ constexpr unsigned kCountMask = 0x3fffffffu;   // last-level counts carry a flag
 constexpr unsigned kBounded = 0x40000000u;     // no tree below this item can enter the ranked list
 // what a scan adds up: the plain count, or (last level) the trees of the items that are not bounded, i.e.
 // an upper bound on the candidates a chunk can append
+__device__ __forceinline__ unsigned scan_value(unsigned x, int live_only) {
+    return (live_only && (x & kBounded)) ? 0u : x & kCountMask;
+}
 // Live mode with the stored bounds (last level): an item whose base's bound exceeds what the CURRENT threshold
 // admits yields no candidate either -- the same test leaf_kernel applies before it touches the item -- so the chunk
 // extends over everything a burst earlier in the fill has made hopeless.
@@ -1174,11 +1172,7 @@ template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__restrict__ fit, long long item_base,
             const unsigned *__restrict__ lcnt, const double *__restrict__ lbound, int part, TopMeta *meta,
-            int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len_arg, int sample_stride,
-            unsigned long long *__restrict__ sample_keys, unsigned sample_min_trees) {
-    // SAMPLE mode (sample_stride > 0): only every sample_stride-th item of the chunk is evaluated and only the score
-    // bits of its candidates are written (sample_keys); chunks with few live trees are not sampled at all.
-    if (sample_stride > 0 && (unsigned)(fit->fit & 0xffffffffull) < sample_min_trees) return;
+            int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len_arg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
@@ -1226,7 +1220,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
         Cand e;
         e.score = INFINITY; e.seq = 0x7fffffffffffffffll; e.part = 0x7fffffff; e.origin = 0xffffffffu; e.pstar = 0; e.pad = 1;
         for (unsigned long long sl = from + lane; sl < to; sl += 32)
-            if ((long long)sl < cand_cap) { if (sample_stride > 0) sample_keys[sl] = ~0ull; else cands[sl] = e; }
+            if ((long long)sl < cand_cap) cands[sl] = e;
     };
     // the chunk: the longest prefix of the pending items whose unbounded trees fit the candidate buffer
     // (scanned on the device just before this launch; the host reads the same number afterwards)
@@ -1253,19 +1247,6 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     bool hopeless = false;
     const bool prune = net.prune != 0 && full;
     const bool prune_pre = prune && !adjacent_only;
-    // Sampled threshold (full pass after a sample pass): only trees whose score is at most the probe can still be
-    // needed, PROVIDED the chunk then yields at least num_save of them (the host checks and repeats the chunk without
-    // the probe otherwise).  tprobe bounds the pre-sqrt total a little generously; the exact test is on the score bits.
-    const unsigned long long probe_bits = sample_stride > 0 ? ~0ull : meta->probe_bits;
-    double tprobe = INFINITY;
-    if (probe_bits != ~0ull) {
-        const double thr = __longlong_as_double((long long)probe_bits);
-        tprobe = __longlong_as_double(__double_as_longlong(__dmul_rn(thr, thr)) + 8);
-    }
-    const double tcut = tprobe < tmax ? tprobe : tmax;      // what a total may be at most
-    unsigned long long my_real = 0;
-    // slots are reserved in batches; behind a probe a warp finds a handful of candidates, not hundreds
-    const unsigned batch = probe_bits != ~0ull ? 32u : (unsigned)kCandBatch;
     const bool has_v = level >= 1;                          // a tree position L-2 exists
     const int wl2 = has_v ? item_byte(level - 1, wstride) >> 2 : 0, sh2 = has_v ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     // The pass mask and the number of valid trees of every item were written by emit2_kernel together with
@@ -1287,8 +1268,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     // not flagged when the level above was checked -- but the threshold has tightened since (a burst earlier in
     // this fill): the base's bound travelled with the item, so the re-test costs one load instead of an evaluation
     bool is_live = (cw & kBounded) == 0;
-    if (is_live && prune_pre && __ldg(lbound + idx) > tcut) is_live = false;
-    if (sample_stride > 0 && (idx % sample_stride) != 0) is_live = false;
+    if (is_live && prune_pre && __ldg(lbound + idx) > tmax) is_live = false;
     unsigned live = __ballot_sync(kFull, is_live);
     {
         const int nblk = run1 - blk < 32 ? (int)(run1 - blk) : 32;
@@ -1381,7 +1361,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
         if (prune && (fresh || (todo[0] | todo[1] | todo[2] | todo[3]))) {
             // new base: its total bounds every tree of the sibling group from below
             const double tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
-            hopeless = tb > tcut;
+            hopeless = tb > tmax;
         }
         if (hopeless) {            // bounded by the current threshold (tighter than the one the level above saw)
             my_bounded++;
@@ -1448,16 +1428,16 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
             // tree of the item is evaluated at once, and only the few that may beat the threshold
             // go through the square root and the append (one slot reservation per group, every lane
             // writes its own tree)
-            const bool cand = ((pqg >> lane) & 1u) && x <= tcut;
+            const bool cand = ((pqg >> lane) & 1u) && x <= tmax;
             const unsigned b = __ballot_sync(kFull, cand);
             if (b) {
                 const unsigned c_n = __popc(b);
                 if (res_end - res_next < c_n) {
                     fill_empty(res_next, res_end);
                     unsigned long long r0 = 0;
-                    if (lane == 0) r0 = atomicAdd(&meta->n_cand, (unsigned long long)batch);
+                    if (lane == 0) r0 = atomicAdd(&meta->n_cand, (unsigned long long)kCandBatch);
                     res_next = __shfl_sync(kFull, r0, 0);
-                    res_end = res_next + batch;
+                    res_end = res_next + kCandBatch;
                 }
                 if (cand) {
                     const unsigned long long slot = res_next + __popc(b & ((1u << lane) - 1u));
@@ -1465,12 +1445,10 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
                         const double score = __dsqrt_rn(x);
                         const unsigned q = g * 32 + lane;
                         Cand c;
-                        const unsigned long long kb = (unsigned long long)__double_as_longlong(score);
-                        const bool keep = (!full || score < tau) && kb <= probe_bits;
-                        if (keep) {
+                        if (!full || score < tau) {
+                            const unsigned long long kb = (unsigned long long)__double_as_longlong(score);
                             kmn = kb < kmn ? kb : kmn;
                             kmx = kb > kmx ? kb : kmx;
-                            my_real++;
                             c.score = score; c.seq = 0; c.part = part;
                             c.origin = (unsigned)(item_base + it);
                             c.pstar = q | ((unsigned)cidx_s[q] << 8);
@@ -1479,8 +1457,7 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
                             c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu;
                             c.pstar = 0; c.pad = 1;
                         }
-                        if (sample_stride > 0) sample_keys[slot] = keep ? kb : ~0ull;
-                        else cands[slot] = c;
+                        cands[slot] = c;
                     }
                 }
                 res_next += c_n;
@@ -1502,9 +1479,6 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
         kmx = b > kmx ? b : kmx;
     }
     if (lane == 0 && kmn <= kmx) { atomicMin(&meta->kmin, kmn); atomicMax(&meta->kmax, kmx); }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) my_real += __shfl_xor_sync(kFull, my_real, d);
-    if (lane == 0 && my_real) atomicAdd(&meta->n_real, my_real);
 }
 
 // Gives every candidate its canonical sequence number (rank among the valid trees) now that the
@@ -1726,7 +1700,7 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
         meta->tau = newc >= (unsigned)num_save ? res[newc - 1].score : INFINITY;
         meta->n_cand = 0;
         meta->n_valid = 0;
-        meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull; meta->probe_bits = ~0ull; meta->n_real = 0;
+        meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull;
     }
 }
 
@@ -1850,15 +1824,13 @@ struct Radix12State {
     int word;                       // 0: digits of the score, 1: digits of seq among the candidates with exactly the threshold score
     int shift, width;               // current digit: bits [shift, shift + width) of the current word; shift < 0: none left
     int seq_rest;                   // low bits in which the sequence numbers of this chunk differ
-    int score_only;                 // only a threshold SCORE is wanted (sample pass): equal scores are not separated
     unsigned done, blocks_done;
     unsigned hist[4096];
 };
 
 __global__ void radix12_init(Radix12State *st, const TopMeta *meta, unsigned long long k, unsigned long long seq_lo,
-                             unsigned long long seq_hi, int score_only) {
+                             unsigned long long seq_hi) {
     if (threadIdx.x == 0) {
-        st->score_only = score_only;
         const unsigned long long kmin = meta->kmin, kmax = meta->kmax;
         st->k = k; st->below = 0; st->kept = 0; st->blocks_done = 0; st->done = 0; st->thresh[0] = st->thresh[1] = 0;
         st->word = 0;
@@ -1873,9 +1845,7 @@ __global__ void radix12_init(Radix12State *st, const TopMeta *meta, unsigned lon
             const int lead = x ? __clzll((long long)x) : 64;
             const int rest = 64 - lead;                 // low bits in which the candidate scores differ
             st->prefix[0] = lead == 0 ? 0ull : lead == 64 ? kmin : kmin & ~(~0ull >> lead);
-            if (rest == 0 && score_only) {              // one score and no need to separate its trees
-                st->done = 1; st->thresh[0] = kmin; st->thresh[1] = ~0ull; st->shift = -1; st->width = 0;
-            } else if (rest == 0) {                     // one score: straight to the sequence numbers
+            if (rest == 0) {                            // one score: straight to the sequence numbers
                 st->word = 1;
                 st->width = st->seq_rest < 12 ? st->seq_rest : 12;
                 st->shift = st->seq_rest == 0 ? -1 : st->seq_rest - st->width;
@@ -1890,9 +1860,8 @@ __global__ void radix12_init(Radix12State *st, const TopMeta *meta, unsigned lon
 
 __global__ void __launch_bounds__(256)
 radix12_pass(const unsigned long long *__restrict__ key0, const unsigned long long *__restrict__ key1, long long m,
-             Radix12State *st, unsigned tile, const unsigned long long *__restrict__ m_dev) {
+             Radix12State *st, unsigned tile) {
     __shared__ unsigned h[4096];
-    if (m_dev) { const long long md = (long long)*m_dev; m = md < m ? md : m; }     // (sample pass: the count is only known on the device)
     __shared__ unsigned part[256];
     __shared__ bool last;
     if (st->done || st->shift < 0) return;              // uniform for the whole grid
@@ -1942,8 +1911,6 @@ radix12_pass(const unsigned long long *__restrict__ key0, const unsigned long lo
             } else if (shift > 0) {
                 const int w = shift < 12 ? shift : 12;
                 st->width = w; st->shift = shift - w;
-            } else if (word == 0 && st->score_only) {
-                st->done = 1; st->thresh[0] = pre; st->thresh[1] = ~0ull;     // the exact score, all its trees
             } else if (word == 0) {
                 // more trees with exactly the threshold score than the tile holds: the sequence numbers decide
                 st->word = 1;
@@ -1974,22 +1941,7 @@ radix12_compact(const Cand *__restrict__ cands, const unsigned long long *__rest
     }
 }
 
-// End of a sample pass: the k-th best sampled score becomes the probe of the full pass over the same chunk, and the
-// counters the sample pass touched are reset.  No probe when the chunk was not sampled or the sample was too small.
-__global__ void sample_finish(TopMeta *meta, const Radix12State *st) {
-    const bool sampled = meta->n_cand > 0;
-    meta->probe_bits = (sampled && st->done) ? st->thresh[0] : ~0ull;
-    meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
-    meta->kmin = ~0ull; meta->kmax = 0ull; meta->n_real = 0;
-}
-
-__global__ void clear_probe(TopMeta *meta) {
-    meta->probe_bits = ~0ull;
-    meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0;
-    meta->kmin = ~0ull; meta->kmax = 0ull; meta->n_real = 0;
-}
-
-__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull; meta->probe_bits = ~0ull; meta->n_real = 0; }
+__global__ void reset_n_cand(TopMeta *meta) { meta->n_cand = 0; meta->n_valid = 0; meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull; }
 
 __global__ void init_meta(TopMeta *meta) {
     meta->count = 0;
@@ -1997,7 +1949,7 @@ __global__ void init_meta(TopMeta *meta) {
     meta->tau = INFINITY;
     meta->n_cand = 0;
     meta->n_valid = 0;
-    meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull; meta->probe_bits = ~0ull; meta->n_real = 0;
+    meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull;
 }
 
 // unpack exported records {score, seq, part, pad, bytes} into Cand entries for a merge
@@ -2175,7 +2127,7 @@ replay_kernel(const __grid_constant__ ReplayArgs a) {
         if (a.first && threadIdx.x == 0) {
             TopMeta *meta = a.meta;
             meta->count = 0; meta->pad = 0; meta->tau = INFINITY; meta->n_cand = 0; meta->n_valid = 0;
-            meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull; meta->probe_bits = ~0ull; meta->n_real = 0;
+            meta->next_run = 0; meta->n_bounded = 0; meta->n_eval = 0; meta->kmin = ~0ull; meta->kmax = 0ull;
         }
         if (threadIdx.x == 0) fuse_count_s = -1;
     }
@@ -2660,10 +2612,6 @@ struct lichee_search {
     Sched *h_sched = nullptr;                // pinned
     bool narrow = true;                      // device-side scheduling of narrow chunks (LICHEE_NO_NARROW=1 turns it off)
     bool no_prefilter = false;               // LICHEE_NO_PREFILTER=1: stored bounds not consulted by the last level and its scan
-    bool no_sample = false;                  // LICHEE_NO_SAMPLE=1: no sampled threshold ahead of large last-level chunks
-    int sample_rank = kSampleRank;           // LICHEE_SAMPLE_RANK / LICHEE_SAMPLE_MIN_ITEMS: test knobs (force the repeat path, sample small chunks)
-    long long sample_min_items = 1 << 14;
-    unsigned sample_min_trees = kSampleMinTrees;
     int flip = 0;
     long long chunk_max = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -2840,13 +2788,13 @@ int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq
     Radix12State *st = static_cast<Radix12State *>(h->b_radix12.p);
     const int grid = (int)std::min<long long>((m + 255) / 256, 148 * 8);
     radix12_init<<<1, 256, 0, h->stream>>>(st, h->d_meta(), (unsigned long long)h->prm.num_save, (unsigned long long)seq_lo,
-                                           (unsigned long long)seq_hi, 0);
+                                           (unsigned long long)seq_hi);
     h->stats.num_launches++;
     h->stats.kernel_launches[LICHEE_K_SELECT]++;
     struct { unsigned long long kept; int shift; unsigned done; } rd{};
     for (int round = 0; round < 2; round++) {           // 6 + 6 digits cover the 128 key bits; finished passes return at once
         const unsigned long long *k0 = static_cast<const unsigned long long *>(h->b_key0.p), *k1 = static_cast<const unsigned long long *>(h->b_key1.p);
-        for (int p = 0; p < 6; p++) radix12_pass<<<grid, 256, 0, h->stream>>>(k0, k1, m, st, (unsigned)kSelTile, nullptr);
+        for (int p = 0; p < 6; p++) radix12_pass<<<grid, 256, 0, h->stream>>>(k0, k1, m, st, (unsigned)kSelTile);
         radix12_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), k0, k1, m, st, h->d_cands(1), (long long)kSelTile);
         CK(cudaGetLastError());
         h->stats.num_launches += 7;
@@ -2945,7 +2893,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             st.num_trees += before.num_trees; st.num_grow_calls += before.num_grow_calls - 1;
             st.num_checks += before.num_checks; st.num_scored += before.num_scored;
             st.num_evaluated += before.num_evaluated; st.num_bounded_items += before.num_bounded_items; st.num_leaf_items += before.num_leaf_items;
-            st.num_sampled_chunks += before.num_sampled_chunks; st.num_probe_repeats += before.num_probe_repeats;
             st.num_launches += before.num_launches; st.frontier_bytes += before.frontier_bytes;
             st.kernel_ms_total += before.kernel_ms_total; st.status |= before.status;
             for (int i = 0; i < LICHEE_NUM_KERNELS; i++) {
@@ -3028,7 +2975,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     // what emit2_kernel reported about the current fill of the last level: items that are not bounded, valid
     // trees below all of them (fill_items = 0: unknown, e.g. after the level was cut into slices)
     long long fill_items = 0, fill_live = 0, fill_trees = 0, fill_parents = 0;
-    long long fill_trees_left = -1;          // valid trees in the part of the current fill not yet processed (-1: unknown)
     bool fill_pending = false;               // emit2's counters are still on their way to the host
     for (;;) {
         int lv = -1;
@@ -3046,7 +2992,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 h->head[lv] = a;
                 h->tail[lv] = b;
                 sliced = true;
-                fill_trees_left = -1;
                 if (a == b) break;
             } else if (h->narrow && lv < L - 2 && width <= kNarrowMax &&
                        width * (long long)h->cands[lv].size() <= std::min<long long>(h->cap, kNarrowCap)) {
@@ -3081,7 +3026,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             fill_pending = false;
             fill_live = (long long)h->h_scan->live;
             fill_trees = (long long)h->h_scan->trees;
-            fill_trees_left = fill_trees;
             // emit2's algorithmic bytes: masks, flag and offset of every parent, a count word per child, and
             // item + mask for the children that are not bounded
             st.kernel_bytes[LICHEE_K_EMIT] += fill_parents * 64ll + fill_items * 4ll + fill_live * (long long)(h->stride + 24);
@@ -3112,7 +3056,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         }
         const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
         const bool dual = lv == L - 2;                       // the level whose children are the last-level items
-        bool sampled = false;                                // last-level chunk: a sample pass set a probe threshold
         if (dual && (ensure(h, h->b_mask2, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_mask3, sizeof(uint4) * (size_t)B) != LICHEE_OK ||
                      ensure(h, h->b_flag, 4 * (size_t)B) != LICHEE_OK || ensure(h, h->b_bound, 8 * (size_t)B) != LICHEE_OK))
             return LICHEE_ERR_CUDA;
@@ -3162,35 +3105,9 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // few instructions, an evaluated one hundreds)
             int run_len = 32;    // (measured: runs of 256 items left a tail of ~1 ms per step; a run of bounded items costs a few instructions)
             if (h->no_prefilter) run_len = -run_len;
-            const double *lb_leaf = static_cast<const double *>(h->b_lbound.p) + h->head[lv];
-            // A chunk that enters a better region beats the stale threshold with millions of trees.  With a full list
-            // and a large chunk, one item in kSampleStride is scored first; the kSampleRank-th best sampled score becomes
-            // the probe of the full pass, which then yields a few thousand candidates instead of millions.  Exact: the
-            // full pass must produce at least num_save candidates (checked below), else the chunk is repeated without it.
-            // (not when MAX_NUM_TREES may fall inside this fill: trees beyond the cap are retired after the launch, so
-            //  neither the sample nor the candidate count below could be trusted)
-            sampled = list_full && h->net.prune && !h->no_sample && B >= h->sample_min_items && fill_trees_left >= 0 &&
-                      seq_base + fill_trees_left < h->prm.max_num_trees;
-            if (sampled) {
-                if (ensure(h, h->b_key0, 8 * (size_t)cand_cap) != LICHEE_OK || ensure(h, h->b_radix12, sizeof(Radix12State)) != LICHEE_OK)
-                    return LICHEE_ERR_CUDA;
-                unsigned long long *skeys = static_cast<unsigned long long *>(h->b_key0.p);
-                Radix12State *rs = static_cast<Radix12State *>(h->b_radix12.p);
-                leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
-                    h->net, items, h->d_scan(), h->head[lv], lcnt, lb_leaf, R, h->d_meta(), h->prm.num_save,
-                    h->d_cands(0), cand_cap, run_len, kSampleStride, skeys, h->sample_min_trees);
-                radix12_init<<<1, 256, 0, h->stream>>>(rs, h->d_meta(), (unsigned long long)h->sample_rank, 0ull, 0ull, 1);
-                for (int p = 0; p < 5; p++)
-                    radix12_pass<<<148 * 2, 256, 0, h->stream>>>(skeys, skeys, cand_cap, rs, (unsigned)kSelTile, &h->d_meta()->n_cand);
-                sample_finish<<<1, 1, 0, h->stream>>>(h->d_meta(), rs);
-                CK(cudaGetLastError());
-                st.num_launches += 8;
-                st.kernel_launches[LICHEE_K_LEAF] += 1;
-                st.kernel_launches[LICHEE_K_SELECT] += 7;
-            }
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
-                h->net, items, h->d_scan(), h->head[lv], lcnt, lb_leaf, R, h->d_meta(), h->prm.num_save,
-                h->d_cands(0), cand_cap, run_len, 0, nullptr, 0u);
+                h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], R, h->d_meta(), h->prm.num_save,
+                h->d_cands(0), cand_cap, run_len);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_LEAF]++;
         }
@@ -3209,20 +3126,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             B = (long long)(h->h_scan->fit >> 32);           // the prefix the kernel took
-            if (sampled && h->h_meta->probe_bits != ~0ull) st.num_sampled_chunks++;
-            if (sampled && h->h_meta->probe_bits != ~0ull && h->h_meta->n_real < (unsigned long long)h->prm.num_save) {
-                // the probe left fewer than num_save candidates: it may have cut off trees that count.  Once more, without it.
-                clear_probe<<<1, 1, 0, h->stream>>>(h->d_meta());
-                leaf_kernel<SPL><<<grid_for(B), kThreads, h->smem_leaf, h->stream>>>(
-                    h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], R,
-                    h->d_meta(), h->prm.num_save, h->d_cands(0), cand_cap, h->no_prefilter ? -32 : 32, 0, nullptr, 0u);
-                CK(cudaGetLastError());
-                st.num_launches += 2;
-                st.kernel_launches[LICHEE_K_LEAF]++;
-                st.num_probe_repeats++;
-                CK(cudaMemcpyAsync(h->h_meta, h->d_meta(), sizeof(TopMeta), cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaStreamSynchronize(h->stream));
-            }
             if (B < 1 || h->h_meta->n_cand > (unsigned long long)cand_cap) {
                 set_err("last-level chunk accounting broken: %lld items, %llu candidates for %lld slots", B,
                         (unsigned long long)h->h_meta->n_cand, cand_cap);
@@ -3231,7 +3134,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             long long m = (long long)h->h_meta->n_cand;
             leaf_total = (long long)h->h_meta->n_valid;
             list_full = h->h_meta->count >= (unsigned)h->prm.num_save || m >= (long long)h->prm.num_save;
-            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld bounded=%llu tau=%.17g count=%u sampled=%d probe=%016llx real=%llu left=%lld\n", B, m, leaf_total, h->h_meta->n_bounded, h->h_meta->tau, h->h_meta->count, (int)sampled, h->h_meta->probe_bits, h->h_meta->n_real, fill_trees_left);
+            if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf chunk B=%lld cand=%lld total=%lld bounded=%llu tau=%.17g count=%u\n", B, m, leaf_total, h->h_meta->n_bounded, h->h_meta->tau, h->h_meta->count);
             CK(cudaEventRecord(h->evk[es][3], h->stream));
             // algorithmic bytes of the launch: the count word of every item, the item itself where it was
             // evaluated, the candidate records written
@@ -3265,7 +3168,6 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             CK(cudaEventRecord(h->evk[es][4], h->stream));
             h->evn[es] = 5;
             const long long total = leaf_total;
-            if (fill_trees_left >= 0) fill_trees_left = std::max<long long>(0, fill_trees_left - total);
             st.num_checks += B * kcand;
             st.num_grow_calls += total;
             st.frontier_bytes += B * (long long)h->stride;
@@ -3773,9 +3675,6 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->h_rout = reinterpret_cast<ReplayOut *>(h->h_sched + 1);
     h->narrow = getenv("LICHEE_NO_NARROW") == nullptr;
     h->no_prefilter = getenv("LICHEE_NO_PREFILTER") != nullptr;
-    h->no_sample = getenv("LICHEE_NO_SAMPLE") != nullptr || h->no_prefilter;
-    if (const char *e = getenv("LICHEE_SAMPLE_RANK")) h->sample_rank = std::max(1, atoi(e));
-    if (const char *e = getenv("LICHEE_SAMPLE_MIN_ITEMS")) { h->sample_min_items = std::max(1, atoi(e)); h->sample_min_trees = 1; }
     h->net.vaf = reinterpret_cast<const double *>(nb);
     h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
     h->net.leaf_static = reinterpret_cast<const double *>(nb + o_ls);

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_struct_layouts_match_the_header(built):
     import lichee_b200
     assert ctypes.sizeof(lichee_b200.SearchParams) == 8 + 4 + 4 + 8 + 8 + 4 + 4 + 8 + 32
-    assert ctypes.sizeof(lichee_b200.SearchStats) == 6 * 8 + 8 + 3 * 5 * 8 + 8 + 5 * 8
+    assert ctypes.sizeof(lichee_b200.SearchStats) == 6 * 8 + 8 + 3 * 5 * 8 + 8 + 3 * 8
     p = lichee_b200.default_params()
     assert (p.vaf_error_margin, p.num_save, p.max_num_trees, p.max_num_grow_calls) == (0.1, 1, 100000, 100000000)
 

@@ -83,36 +83,3 @@ def test_config3_identical_to_the_reference_with_a_large_budget(built):
     h.update(np.array([t.treeNodes for t in trees], dtype=np.int32).tobytes())
     h.update(np.array([t.seq for t in trees], dtype=np.int64).tobytes())
     assert h.hexdigest() == ref["top100_sha256"]
-
-
-def test_sampled_threshold_and_its_repeat_path(built, monkeypatch):
-    """Large last-level chunks are scored behind a threshold taken from a 1-in-16 sample of their items; when that
-    leaves fewer than num_save candidates the chunk is repeated without it.  Test knobs make mid-size searches take
-    both paths (sampling from 256-item chunks on; rank 1 = the best sampled score as the probe, which almost always
-    leaves too few candidates): ranked lists, scores, sequence numbers and counts must equal the unsampled search."""
-    import lichee_b200
-    # (sampling is only allowed where MAX_NUM_TREES cannot fall inside the fill: exhaustive searches and long capped ones)
-    cases = [(make_instance(12, 5, seed=4), 64, 10**9), (make_instance(40, 20, seed=2026), 1000, 1 << 25),
-             (make_instance(13, 40, seed=3), 300, 10**9), (make_instance(30, 12, seed=7), 25, 1 << 24)]
-    took_probe = took_repeat = 0
-    for (net, prm), save, cap in cases:
-        results = []
-        for env in ({"LICHEE_NO_SAMPLE": "1"}, {"LICHEE_SAMPLE_MIN_ITEMS": "256"},
-                    {"LICHEE_SAMPLE_MIN_ITEMS": "256", "LICHEE_SAMPLE_RANK": "1"}):
-            for k in ("LICHEE_NO_SAMPLE", "LICHEE_SAMPLE_MIN_ITEMS", "LICHEE_SAMPLE_RANK"):
-                monkeypatch.delenv(k, raising=False)
-            for k, v in env.items():
-                monkeypatch.setenv(k, v)
-            s = lichee_b200.LineageSearch(net.adj, np.array(net.aaf), prm.vaf_error_margin, num_save=save, max_num_trees=cap,
-                                          max_num_grow_calls=1 << 62, ref_order_budget=-1)
-            st = s.run()
-            results.append((int(st.num_trees), lichee_b200.top_list_sha256(s.trees())))
-            if "LICHEE_SAMPLE_RANK" in env:
-                took_repeat += int(st.num_probe_repeats)
-            elif "LICHEE_SAMPLE_MIN_ITEMS" in env:
-                took_probe += int(st.num_sampled_chunks)
-            s.close()
-        assert results[1] == results[0] and results[2] == results[0], (net.n, results)
-    for k in ("LICHEE_NO_SAMPLE", "LICHEE_SAMPLE_MIN_ITEMS", "LICHEE_SAMPLE_RANK"):
-        monkeypatch.delenv(k, raising=False)
-    assert took_probe > 0 and took_repeat > 0
