@@ -183,3 +183,20 @@ def test_rerun_and_one_shot_entry_point(built):
     m = int(st.num_saved)
     assert list(sc[:m]) == list(ref["scores"]) and par[:m].tolist() == ref["parents"].tolist()
     assert order[:m].tolist() == ref["orders"].tolist()
+
+
+def test_largest_network_state_in_global_memory(built):
+    """128 nodes x 64 samples, complete DAG (8128 edges): the replay's state no longer fits shared memory next to the
+    centroid matrix and is worked on in place in global memory; four 32-node groups, two samples per lane.  The
+    reference's search of such a network never ends, so both sides stop at MAX_NUM_GROW_CALLS = 20000: the trees found
+    until then (1295, all tied at score 0) must be the reference's, in the reference's order."""
+    n, S = 128, 64
+    rng = np.random.RandomState(5)
+    vaf = np.full((n, S), 0.003) + 1e-5 * rng.rand(n, S)
+    vaf[0, :] = 0.5
+    vaf[1:8, :] = 0.02
+    adj = [[j for j in range(i + 1, n)] for i in range(n)]
+    for a in adj:
+        rng.shuffle(a)
+    st, trees, ref = assert_identical_to_reference(adj, vaf, -0.001, 50, max_trees=3000, max_grow=20000)
+    assert st["num_trees"] == ref["n_trees"] > 1000 and st["status"] & 2
