@@ -217,6 +217,11 @@ __device__ __forceinline__ void parent_presence(unsigned w, int rmax, unsigned p
     pm[3] = __reduce_or_sync(kFull, m3);
 }
 
+__device__ __forceinline__ bool get_bit(const uint4 &m, unsigned i) {
+    const unsigned w = (i >> 5) == 0 ? m.x : (i >> 5) == 1 ? m.y : (i >> 5) == 2 ? m.z : m.w;
+    return ((w >> (i & 31)) & 1u) != 0;
+}
+
 // Sum rule for candidate row q that already has children in item w: children + the new node (row
 // xv) against VAF(q) + margin in every sample.  One copy of the code (the kernels call it from
 // several unrolled places; inlined, they outgrow the instruction cache).
@@ -684,20 +689,28 @@ descend_kernel(DevNet net, Sched *sc) {
         }
         __syncthreads();
 
-        // check: a task is (item, slice of the candidate list); few items -> more slices per item.  Every
-        // candidate goes through the sums (a candidate without children gives 0 + VAF(node) against
-        // VAF(parent) + margin, the same doubles as the static bit of the wide kernels).
+        // check: a task is (item, slice of the candidate list); few items -> more slices per item (a single item is
+        // split over all 32 warps).
         int lp = 0;
-        while (lp < 3 && (B << (lp + 1)) <= 2 * kNarrowWarps && (2 << lp) <= k) lp++;
+        while (lp < 5 && (B << (lp + 1)) <= 2 * kNarrowWarps && (2 << lp) <= k) lp++;
+        const uint4 sok4 = net.static_ok[lv];
         for (int task = wid; task < (B << lp); task += kNarrowWarps) {
             const int it = task >> lp, part = task & ((1 << lp) - 1);
             const int c0 = (k * part) >> lp, c1 = (k * (part + 1)) >> lp;
             const unsigned w = lane < W ? item_s[it * 32 + lane] : 0xffffffffu;
             double xv0, xv1;
             load_row<SPL>(vaf_s, lv + 1, SP, lane, xv0, xv1);
+            unsigned pm[4];
+            parent_presence(w, rmax, pm);
             unsigned long long blo = 0, bhi = 0;
             for (int j = c0; j < c1; j++) {
-                const bool pass = row_passes<SPL>(w, cand_s[j], rmax, W, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1);
+                // a candidate without a child in the item: the precomputed answer (the same doubles, 0 + VAF(node)
+                // against VAF(parent) + margin)
+                const unsigned q = cand_s[j];
+                const unsigned pw = (q >> 5) == 0 ? pm[0] : (q >> 5) == 1 ? pm[1] : (q >> 5) == 2 ? pm[2] : pm[3];
+                const bool pass = ((pw >> (q & 31)) & 1u)
+                                      ? row_passes<SPL>(w, q, rmax, W, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1)
+                                      : get_bit(sok4, (unsigned)j);
                 const unsigned long long bit = (unsigned long long)(pass ? 1u : 0u) << (j & 63);
                 if (j < 64) blo |= bit; else bhi |= bit;
             }
@@ -889,10 +902,6 @@ __device__ __forceinline__ void put_bit(unsigned m[4], unsigned i, bool v) {
     m[2] = g == 2 ? (v ? m[2] | bit : m[2] & ~bit) : m[2];
     m[3] = g == 3 ? (v ? m[3] | bit : m[3] & ~bit) : m[3];
 }
-__device__ __forceinline__ bool get_bit(const uint4 &m, unsigned i) {
-    const unsigned w = (i >> 5) == 0 ? m.x : (i >> 5) == 1 ? m.y : (i >> 5) == 2 ? m.z : m.w;
-    return ((w >> (i & 31)) & 1u) != 0;
-}
 
 // ------------------------------------------------------------------------------------------
 // kernels 1b / 3c: the level above the last one.  Its items are the BASES of the last level: the
@@ -982,75 +991,111 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
 
-    // per base item: bv = v fits (by v's candidate index), bb = v and u both fit (same index), bu = u fits
-    // without v (by u's candidate index), um = rows present, E = excess of the rows (lane l: rows l, l+32, ..)
-    unsigned bv[4] = {0, 0, 0, 0}, bb[4] = {0, 0, 0, 0}, bu[4] = {0, 0, 0, 0}, um[4] = {0, 0, 0, 0};
-    double E[4] = {0.0, 0.0, 0.0, 0.0};
-    unsigned w_prev = 0;
+    // Neighbouring items are the children of one item of the level above: they differ only in where its node x (tree
+    // position L-3, the highest assigned one) hangs.  The state is therefore kept for the item WITHOUT x -- per row:
+    // bv0 = v fits (by v's candidate index), bb0 = v and u both fit (same index), bu0 = u fits without v (by u's
+    // candidate index), um0 = rows present, E0 = excess of the rows (lane l: rows l, l+32, ..) -- and updated only
+    // when a byte other than x's changes (a new sibling group); on top of it ONE row per item is decided with x in
+    // place: the parent p that x hangs under (x is the last child in p's sums, the same additions as a full
+    // evaluation of the item).
+    unsigned bv0[4] = {0, 0, 0, 0}, bb0[4] = {0, 0, 0, 0}, bu0[4] = {0, 0, 0, 0}, um0[4] = {0, 0, 0, 0};
+    double E0[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned wb_prev = 0;
+    const bool has_x = level >= 1;
+    const int wl3 = has_x ? item_byte(level - 1, wstride) >> 2 : 0, sh3 = has_x ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
     for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len) {
         const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
+        unsigned w_next = lane < wstride ? __ldg(items + run0 * wstride + lane) : 0xffffffffu;
         for (long long it = run0; it < run1; it++) {
-            const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
+            const unsigned w = w_next;
+            if (it + 1 < run1) w_next = lane < wstride ? __ldg(items + (it + 1) * wstride + lane) : 0xffffffffu;
+            const unsigned wb = (has_x && lane == wl3) ? (w | (0xffu << sh3)) : w;     // the item with x taken out
             bool fresh = it == run0;
             unsigned todo[4] = {0, 0, 0, 0};
             if (!fresh) {
-                unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-                const unsigned diff = w ^ w_prev;
-                for (int r = 0; r <= rmax; r++) {
-                    if ((diff >> (8 * r)) & 0xffu) {
-                        const unsigned bo = (w_prev >> (8 * r)) & 0xffu, bn = (w >> (8 * r)) & 0xffu;
-                        const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
-                        c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
-                        c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
-                        c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
-                        c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+                const unsigned diff = wb ^ wb_prev;
+                if (__any_sync(kFull, diff != 0)) {
+                    unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                    for (int r = 0; r <= rmax; r++) {
+                        if ((diff >> (8 * r)) & 0xffu) {
+                            const unsigned bo = (wb_prev >> (8 * r)) & 0xffu, bn = (wb >> (8 * r)) & 0xffu;
+                            const unsigned bito = bo < 128u ? 1u << (bo & 31) : 0u, bitn = bn < 128u ? 1u << (bn & 31) : 0u;
+                            c0 |= ((bo >> 5) == 0 ? bito : 0u) | ((bn >> 5) == 0 ? bitn : 0u);
+                            c1 |= ((bo >> 5) == 1 ? bito : 0u) | ((bn >> 5) == 1 ? bitn : 0u);
+                            c2 |= ((bo >> 5) == 2 ? bito : 0u) | ((bn >> 5) == 2 ? bitn : 0u);
+                            c3 |= ((bo >> 5) == 3 ? bito : 0u) | ((bn >> 5) == 3 ? bitn : 0u);
+                        }
                     }
+                    todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
+                    todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
+                    if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
                 }
-                todo[0] = __reduce_or_sync(kFull, c0); todo[1] = __reduce_or_sync(kFull, c1);
-                todo[2] = __reduce_or_sync(kFull, c2); todo[3] = __reduce_or_sync(kFull, c3);
-                if (__popc(todo[0]) + __popc(todo[1]) + __popc(todo[2]) + __popc(todo[3]) > kMaxIncremental) fresh = true;
             }
-            w_prev = w;
+            wb_prev = wb;
             if (fresh) {
-                parent_presence(w, rmax, um);
+                parent_presence(wb, rmax, um0);
                 // every candidate starts childless (static answers); present rows overwrite theirs below
-                bv[0] = sokv.x; bv[1] = sokv.y; bv[2] = sokv.z; bv[3] = sokv.w;
-                bb[0] = sboth.x; bb[1] = sboth.y; bb[2] = sboth.z; bb[3] = sboth.w;
-                bu[0] = soku.x; bu[1] = soku.y; bu[2] = soku.z; bu[3] = soku.w;
+                bv0[0] = sokv.x; bv0[1] = sokv.y; bv0[2] = sokv.z; bv0[3] = sokv.w;
+                bb0[0] = sboth.x; bb0[1] = sboth.y; bb0[2] = sboth.z; bb0[3] = sboth.w;
+                bu0[0] = soku.x; bu0[1] = soku.y; bu0[2] = soku.z; bu0[3] = soku.w;
             }
+            if (fresh || (todo[0] | todo[1] | todo[2] | todo[3])) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                unsigned rows;
-                if (fresh) {
-                    E[g] = 0.0;
-                    rows = prune ? um[g] : um[g] & (candq[g] | candq2[g]);
-                } else {
-                    rows = todo[g];
-                }
-                while (rows) {
-                    const int bq = __ffs(rows) - 1;
-                    rows &= rows - 1;
-                    const unsigned q = g * 32 + bq;
-                    if (!fresh) {
-                        const bool here = __ballot_sync(kFull, __vcmpeq4(w, q * 0x01010101u) != 0) != 0;
-                        um[g] = here ? um[g] | (1u << bq) : um[g] & ~(1u << bq);
-                    }
-                    const bool is_cv = ((candq[g] >> bq) & 1u) != 0, is_cu = ((candq2[g] >> bq) & 1u) != 0;
-                    const unsigned iv = cidx_s[q], iu = cidx2_s[q];
-                    double Eq = 0.0;
-                    unsigned r;
-                    if ((um[g] >> bq) & 1u) {
-                        r = (prune || is_cv || is_cu)
-                                ? dual_row<SPL>(w, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, xu0, xu1, net.margin, valid0,
-                                                valid1, is_cv, is_cu, prune, Eq)
-                                : 0u;
+                for (int g = 0; g < 4; g++) {
+                    unsigned rows;
+                    if (fresh) {
+                        E0[g] = 0.0;
+                        rows = prune ? um0[g] : um0[g] & (candq[g] | candq2[g]);
                     } else {
-                        r = (is_cv && get_bit(sokv, iv) ? 1u : 0u) | (is_cv && get_bit(sboth, iv) ? 2u : 0u) |
-                            (is_cu && get_bit(soku, iu) ? 4u : 0u);
+                        rows = todo[g];
                     }
-                    if (lane == bq) E[g] = Eq;
-                    if (is_cv) { put_bit(bv, iv, (r & 1u) != 0); put_bit(bb, iv, (r & 2u) != 0); }
-                    if (is_cu) put_bit(bu, iu, (r & 4u) != 0);
+                    while (rows) {
+                        const int bq = __ffs(rows) - 1;
+                        rows &= rows - 1;
+                        const unsigned q = g * 32 + bq;
+                        if (!fresh) {
+                            const bool here = __ballot_sync(kFull, __vcmpeq4(wb, q * 0x01010101u) != 0) != 0;
+                            um0[g] = here ? um0[g] | (1u << bq) : um0[g] & ~(1u << bq);
+                        }
+                        const bool is_cv = ((candq[g] >> bq) & 1u) != 0, is_cu = ((candq2[g] >> bq) & 1u) != 0;
+                        const unsigned iv = cidx_s[q], iu = cidx2_s[q];
+                        double Eq = 0.0;
+                        unsigned r;
+                        if ((um0[g] >> bq) & 1u) {
+                            r = (prune || is_cv || is_cu)
+                                    ? dual_row<SPL>(wb, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, xu0, xu1, net.margin, valid0,
+                                                    valid1, is_cv, is_cu, prune, Eq)
+                                    : 0u;
+                        } else {
+                            r = (is_cv && get_bit(sokv, iv) ? 1u : 0u) | (is_cv && get_bit(sboth, iv) ? 2u : 0u) |
+                                (is_cu && get_bit(soku, iu) ? 4u : 0u);
+                        }
+                        if (lane == bq) E0[g] = Eq;
+                        if (is_cv) { put_bit(bv0, iv, (r & 1u) != 0); put_bit(bb0, iv, (r & 2u) != 0); }
+                        if (is_cu) put_bit(bu0, iu, (r & 4u) != 0);
+                    }
+                }
+            }
+            // the one row that sees x: its parent p in this item
+            unsigned bv[4] = {bv0[0], bv0[1], bv0[2], bv0[3]}, bb[4] = {bb0[0], bb0[1], bb0[2], bb0[3]};
+            unsigned bu[4] = {bu0[0], bu0[1], bu0[2], bu0[3]};
+            double E[4] = {E0[0], E0[1], E0[2], E0[3]};
+            if (has_x) {
+                const unsigned p = (__shfl_sync(kFull, w, wl3) >> sh3) & 0xffu;
+                const unsigned gp = p >> 5, bp = p & 31;
+                const unsigned cq = gp == 0 ? candq[0] : gp == 1 ? candq[1] : gp == 2 ? candq[2] : candq[3];
+                const unsigned cq2 = gp == 0 ? candq2[0] : gp == 1 ? candq2[1] : gp == 2 ? candq2[2] : candq2[3];
+                const bool is_cv = ((cq >> bp) & 1u) != 0, is_cu = ((cq2 >> bp) & 1u) != 0;
+                if (prune || is_cv || is_cu) {
+                    double Eq = 0.0;
+                    const unsigned r = dual_row<SPL>(w, p, rmax, wstride, vaf_s, SP, lane, xv0, xv1, xu0, xu1, net.margin, valid0,
+                                                     valid1, is_cv, is_cu, prune, Eq);
+                    if (is_cv) { const unsigned iv = cidx_s[p]; put_bit(bv, iv, (r & 1u) != 0); put_bit(bb, iv, (r & 2u) != 0); }
+                    if (is_cu) put_bit(bu, cidx2_s[p], (r & 4u) != 0);
+                    if (lane == (int)bp) {
+                        E[0] = gp == 0 ? Eq : E[0]; E[1] = gp == 1 ? Eq : E[1];
+                        E[2] = gp == 2 ? Eq : E[2]; E[3] = gp == 3 ? Eq : E[3];
+                    }
                 }
             }
             unsigned flag = 0;
@@ -1100,27 +1145,34 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     unsigned long long my_trees = 0, my_live = 0;       // per lane, reduced at the end
+    // the next base's words are requested while this one is written (the loop is bound by their latency)
+    uint4 m4n = make_uint4(0, 0, 0, 0), mbn = m4n, mun = m4n;
+    unsigned fln = 0, offn = 0;
+    if (warp0 < n_items) { m4n = mask[warp0]; mbn = both[warp0]; mun = masku[warp0]; fln = flag[warp0]; offn = off[warp0]; }
     for (long long it = warp0; it < n_items; it += nwarps) {
-        const uint4 m4 = mask[it];
+        const uint4 m4 = m4n, mb = mbn, mu = mun;
+        const unsigned fl = fln ? kBounded : 0u;
+        long long dst = (long long)offn;
+        if (it + nwarps < n_items) {
+            const long long nx = it + nwarps;
+            m4n = mask[nx]; mbn = both[nx]; mun = masku[nx]; fln = flag[nx]; offn = off[nx];
+        }
         if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
-        const uint4 mb = both[it], mu = masku[it];
-        const unsigned fl = flag[it] ? kBounded : 0u;
-        long long dst = (long long)off[it];
         const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
         if (fl) {
             // bounded base: nobody will read its children, only their tree counts are needed (for the number
-            // of valid trees and the sequence numbers of later candidates).  One child per lane, no item bytes.
+            // of valid trees and the sequence numbers of later candidates).  Lane j owns candidate g*32+j: where its
+            // bit is set it writes the count of that child at the child's rank among the set bits.  No item bytes.
             const unsigned n_u = __popc(mu.x) + __popc(mu.y) + __popc(mu.z) + __popc(mu.w);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 const unsigned b = mw[g];
-                const unsigned pos = __fns(b, 0, lane + 1);          // lane-th set bit of the group
-                if (pos < 32u) {
-                    const unsigned i = g * 32 + pos, q = cand_s[i];
+                if ((b >> lane) & 1u) {
+                    const unsigned i = g * 32 + lane, q = cand_s[i];
                     unsigned cnt = n_u;
                     if ((candq2_s[q >> 5] >> (q & 31)) & 1u)
                         cnt = cnt - (get_bit(mu, cidx2_s[q]) ? 1u : 0u) + (get_bit(mb, i) ? 1u : 0u);
-                    lcnt_out[dst + lane] = cnt | fl;
+                    lcnt_out[dst + __popc(b & ((1u << lane) - 1u))] = cnt | fl;
                     my_trees += cnt;
                 }
                 dst += __popc(b);
