@@ -1226,7 +1226,7 @@ template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__restrict__ fit, long long item_base,
             const unsigned *__restrict__ lcnt, const double *__restrict__ lbound, int part, TopMeta *meta,
-            int num_save, Cand *__restrict__ cands, long long cand_cap, int run_len_arg) {
+            int num_save, uint4 *__restrict__ cands, long long cand_cap, int run_len_arg, const unsigned *__restrict__ ref_item) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
     uint8_t *cand_s = reinterpret_cast<uint8_t *>(vaf_s + net.n * net.SP);
@@ -1264,15 +1264,17 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     double tau;
     const double tmax = admit_bound(meta, num_save, full, tau);
     unsigned long long my_valid = 0, my_eval = 0;
-    unsigned long long kmn = ~0ull, kmx = 0ull;   // score bits of the candidates this thread wrote
     unsigned my_bounded = 0;
     // candidate slots are reserved kCandBatch at a time per warp (one atomic on the shared counter per batch,
     // not per tree: in a good region millions of trees beat a stale threshold within one launch); slots a
     // warp does not use are written as empty entries (pad = 1), which every consumer skips
     unsigned long long res_next = 0, res_end = 0;
+    // A candidate leaves this kernel as 16 bytes: {total (the sum of squared excesses, 8 bytes), item, row of the last
+    // node's parent | its candidate index << 8}; item = ~0 marks an empty slot.  seq_fixup_kernel takes the square
+    // root, numbers the tree and writes the 32-byte record and the selection keys (in a good region a third of this
+    // kernel's instructions went into building and storing the full records of millions of trees).
     auto fill_empty = [&](unsigned long long from, unsigned long long to) {
-        Cand e;
-        e.score = INFINITY; e.seq = 0x7fffffffffffffffll; e.part = 0x7fffffff; e.origin = 0xffffffffu; e.pstar = 0; e.pad = 1;
+        const uint4 e = make_uint4(0u, 0x7ff00000u, 0xffffffffu, 0u);
         for (unsigned long long sl = from + lane; sl < to; sl += 32)
             if ((long long)sl < cand_cap) cands[sl] = e;
     };
@@ -1309,6 +1311,53 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     // EVALUATED items only.
     // runs are handed out from a counter, so a warp that drew cheap runs simply draws more of them
     long long last_it = -2;
+    bool have_state = false;
+    // Reference state of the block.  A warp's first evaluated item used to cost a full evaluation of its base (every
+    // present parent row: ~6000 instructions, 40 % of a launch inside a good region).  The bases of one fill share all
+    // but their last few bytes, so the block evaluates ONE base of the fill together -- ref_item: the first item of
+    // the chunk of the level above that this fill came from; every warp takes a 16th of its rows -- and every warp
+    // starts from that state: its first item then redoes only the rows named by the bytes that differ (or falls
+    // back to the full evaluation when those are many).  Same arithmetic per row, so nothing moves in the results.
+    if (ref_item != nullptr && !adjacent_only && has_v) {
+        __shared__ double eref_s[kMaxN], fref_s[kMaxN];
+        __shared__ unsigned passref_s[4];
+        const int wid = threadIdx.x >> 5;
+        unsigned wr = lane < wstride ? __ldg(ref_item + lane) : 0xffffffffu;
+        if (lane == wl2) wr |= 0xffu << sh2;
+        parent_presence(wr, rmax, um);
+        if (threadIdx.x < 4) passref_s[threadIdx.x] = candq[threadIdx.x] & ~(threadIdx.x == 0 ? um[0] : threadIdx.x == 1 ? um[1] : threadIdx.x == 2 ? um[2] : um[3]) & okq[threadIdx.x];
+        __syncthreads();
+        int rank = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            unsigned rows = um[g];
+            while (rows) {
+                const int bq = __ffs(rows) - 1;
+                rows &= rows - 1;
+                if ((rank++ & (kWarpsPerBlock - 1)) != wid) continue;
+                double Eq, Fq;
+                const bool pass = leaf_row<SPL>(wr, g * 32 + bq, rmax, wstride, vaf_s, SP, lane, xv0, xv1, net.margin, valid0, valid1,
+                                                ((candq[g] >> bq) & 1u) != 0, true, Eq, Fq);
+                if (lane == 0) {
+                    eref_s[g * 32 + bq] = Eq;
+                    fref_s[g * 32 + bq] = Fq;
+                    if (pass) atomicOr(&passref_s[g], 1u << bq);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const bool present = ((um[g] >> lane) & 1u) != 0;
+            const bool absent_ok = ((candq[g] & ~um[g] & okq[g]) >> lane) & 1u;
+            passq[g] = passref_s[g];
+            E[g] = present ? eref_s[g * 32 + lane] : 0.0;
+            F[g] = present ? fref_s[g * 32 + lane] : absent_ok ? fstat_s[g * 32 + lane] : 0.0;
+        }
+        wb_prev = wr;
+        have_state = true;
+        if (prune) hopeless = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3]))) > tmax;
+    }
     for (;;) {
     long long run0 = 0;
     if (lane == 0) run0 = (long long)atomicAdd(&meta->next_run, 1ull) * run_len;
@@ -1347,8 +1396,9 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
         // The state belongs to the base of the item evaluated LAST by this warp, wherever that item was: the rows to
         // redo come from the bytes in which the two bases differ, so bounded items in between (97 % of a level on
         // the headline network) do not force a full evaluation of the next live one.
-        bool fresh = last_it < 0 || (adjacent_only && it != last_it + 1);
+        bool fresh = !have_state || (adjacent_only && it != last_it + 1);
         last_it = it;
+        have_state = true;
         if (!fresh) {
             const unsigned diff = wb ^ wb_prev;
             if (__any_sync(kFull, diff != 0)) {
@@ -1494,24 +1544,12 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
                     res_end = res_next + kCandBatch;
                 }
                 if (cand) {
+                    // (x <= tmax already says that the rounded square root is below the threshold: admit_bound)
                     const unsigned long long slot = res_next + __popc(b & ((1u << lane) - 1u));
                     if ((long long)slot < cand_cap) {
-                        const double score = __dsqrt_rn(x);
                         const unsigned q = g * 32 + lane;
-                        Cand c;
-                        if (!full || score < tau) {
-                            const unsigned long long kb = (unsigned long long)__double_as_longlong(score);
-                            kmn = kb < kmn ? kb : kmn;
-                            kmx = kb > kmx ? kb : kmx;
-                            c.score = score; c.seq = 0; c.part = part;
-                            c.origin = (unsigned)(item_base + it);
-                            c.pstar = q | ((unsigned)cidx_s[q] << 8);
-                            c.pad = 0;
-                        } else {            // rounded square root not below the threshold after all: an empty slot
-                            c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu;
-                            c.pstar = 0; c.pad = 1;
-                        }
-                        cands[slot] = c;
+                        const long long xb = __double_as_longlong(x);
+                        cands[slot] = make_uint4((unsigned)xb, (unsigned)(xb >> 32), (unsigned)(item_base + it), q | ((unsigned)cidx_s[q] << 8));
                     }
                 }
                 res_next += c_n;
@@ -1526,43 +1564,62 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     if (lane == 0 && my_valid) atomicAdd(&meta->n_valid, my_valid);
     if (lane == 0 && my_bounded) atomicAdd(&meta->n_bounded, (unsigned long long)my_bounded);
     if (lane == 0 && my_eval) atomicAdd(&meta->n_eval, my_eval);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const unsigned long long a = __shfl_xor_sync(kFull, kmn, d), b = __shfl_xor_sync(kFull, kmx, d);
-        kmn = a < kmn ? a : kmn;
-        kmx = b > kmx ? b : kmx;
-    }
-    if (lane == 0 && kmn <= kmx) { atomicMin(&meta->kmin, kmn); atomicMax(&meta->kmax, kmx); }
 }
 
-// Gives every candidate its canonical sequence number (rank among the valid trees) now that the
-// scan has numbered the items, and retires the ones beyond Parameters.MAX_NUM_TREES.
-// Also writes the selection keys as two plain arrays (score bits, seq; ~0 for an empty slot): the radix passes
-// then read 8 or 16 bytes per candidate instead of the 32-byte record.
-__global__ void seq_fixup_kernel(Cand *cands, long long m, long long item_base, const uint4 *__restrict__ mask,
-                                 const unsigned *__restrict__ off, long long seq_base, long long max_trees,
-                                 unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1) {
+// Turns the 16-byte candidates of leaf_kernel into ranked-list records: score = sqrt_rn(total), the canonical sequence
+// number (rank among the valid trees) now that the scan has numbered the items; retires the ones beyond
+// Parameters.MAX_NUM_TREES.  Also writes the selection keys (score bits, seq; ~0 for an empty slot) as two plain
+// arrays -- the radix passes then read 8 or 16 bytes per candidate instead of the 32-byte record -- and records the
+// smallest and largest score bits of the launch (where the radix passes start).
+__global__ void __launch_bounds__(256)
+seq_fixup_kernel(const uint4 *__restrict__ c16, Cand *__restrict__ cands, long long m, long long item_base,
+                 const uint4 *__restrict__ mask, const unsigned *__restrict__ off, long long seq_base, long long max_trees,
+                 unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1, TopMeta *meta, int num_save, int part) {
+    __shared__ unsigned long long mn_s[8], mx_s[8];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    Cand c = cands[t];
-    if (c.pad) { key0[t] = ~0ull; key1[t] = ~0ull; return; }
-    const long long it = (long long)c.origin - item_base;
-    const unsigned i = c.pstar >> 8;
-    const uint4 m4 = mask[it];
-    const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
-    unsigned rank = 0;
-    for (unsigned g = 0; g < (i >> 5); g++) rank += __popc(mw[g]);
-    rank += __popc(mw[i >> 5] & ((1u << (i & 31)) - 1u));
-    const long long seq = seq_base + (long long)off[it] + rank;
-    c.pstar &= 0xffu;
-    if (seq >= max_trees) {
-        c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu; c.pad = 1;
-        key0[t] = ~0ull; key1[t] = ~0ull;
-    } else {
-        c.seq = seq;
-        key0[t] = (unsigned long long)__double_as_longlong(c.score); key1[t] = (unsigned long long)seq;
+    unsigned long long kb = ~0ull, seqk = ~0ull;
+    bool live = false;
+    Cand c;
+    c.score = INFINITY; c.seq = 0x7fffffffffffffffll; c.part = 0x7fffffff; c.origin = 0xffffffffu; c.pstar = 0; c.pad = 1;
+    if (t < m) {
+        const uint4 r = c16[t];
+        if (r.z != 0xffffffffu) {
+            const double x = __longlong_as_double((long long)(((unsigned long long)r.y << 32) | r.x));
+            const double score = __dsqrt_rn(x);
+            const long long it = (long long)r.z - item_base;
+            const unsigned i = r.w >> 8;
+            const uint4 m4 = mask[it];
+            const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
+            unsigned rank = 0;
+            for (unsigned g = 0; g < (i >> 5); g++) rank += __popc(mw[g]);
+            rank += __popc(mw[i >> 5] & ((1u << (i & 31)) - 1u));
+            const long long seq = seq_base + (long long)off[it] + rank;
+            // (a full list admits only scores below its threshold: leaf_kernel's bound on the total says the same)
+            const bool admitted = meta->count < (unsigned)num_save || score < meta->tau;
+            if (seq < max_trees && admitted) {
+                live = true;
+                kb = (unsigned long long)__double_as_longlong(score);
+                seqk = (unsigned long long)seq;
+                c.score = score; c.seq = seq; c.part = part; c.origin = r.z; c.pstar = r.w & 0xffu; c.pad = 0;
+            }
+        }
+        key0[t] = kb; key1[t] = seqk;
+        cands[t] = c;
     }
-    cands[t] = c;
+    // key range of the launch: one pair of atomics per block
+    unsigned long long mn = live ? kb : ~0ull, mx = live ? kb : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(kFull, mn, d), b = __shfl_xor_sync(kFull, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { mn_s[threadIdx.x >> 5] = mn; mx_s[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { mn = mn_s[w] < mn ? mn_s[w] : mn; mx = mx_s[w] > mx ? mx_s[w] : mx; }
+        if (mn <= mx) { atomicMin(&meta->kmin, mn); atomicMax(&meta->kmax, mx); }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2658,6 +2715,7 @@ struct lichee_search {
     DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_radix12, b_key0, b_key1, b_cands[2], b_top[2], b_tree[2];
     DevBuf b_mask2, b_mask3, b_flag, b_bound; // level L-2 chunks: "v and u" mask, "u without v" mask, bounded flag, bound value
     DevBuf b_lmask, b_lcnt, b_lbound;        // last level, parallel to its item buffer: pass mask, count | flags, bound of the base
+    DevBuf b_c16;                            // 16-byte candidates of the running last-level launch (leaf_kernel -> seq_fixup_kernel)
     uint4 sok_last{};                        // static pass mask of the last node (n == 2: the only item's mask)
     DevBuf b_slab;                           // kNarrowCap items for every level (what the narrow scheduler emits into)
     DevBuf b_sched;                          // Sched, device copy
@@ -3030,6 +3088,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     // trees below all of them (fill_items = 0: unknown, e.g. after the level was cut into slices)
     long long fill_items = 0, fill_live = 0, fill_trees = 0, fill_parents = 0;
     bool fill_pending = false;               // emit2's counters are still on their way to the host
+    const unsigned *fill_ref = nullptr;      // an item of the level above from the chunk the current fill came from (leaf_kernel's reference base)
     for (;;) {
         int lv = -1;
         if (!sliced) {
@@ -3097,6 +3156,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * (double)fill_trees / (double)B : (double)fill_trees / (double)B;
             seen[lv] = true;
             h->head[lv] = h->tail[lv] = 0;
+            fill_ref = nullptr;
             if (getenv("LICHEE_DEBUG")) fprintf(stderr, "leaf fill B=%lld counted only: %lld trees\n", B, fill_trees);
             if (seq_base >= h->prm.max_num_trees) { st.status |= LICHEE_STATUS_TREE_CAP; break; }
             if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
@@ -3145,7 +3205,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             // the chunk may become a candidate, so the chunk is the longest prefix of the pending items whose
             // unbounded trees fit the candidate buffer: scanned on the device, read by the kernel from
             // device memory and by the host afterwards (no round trip in between, no overflow possible).
-            if (ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            if (ensure(h, h->b_c16, sizeof(uint4) * (size_t)cand_cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
             // (slots are reserved in batches: up to 31 of every 256 and one batch per warp may stay empty)
             // (while the ranked list is still filling up every tree is a candidate, so the first chunk stays small,
             //  yet large enough for a whole search under the reference's MAX_NUM_TREES = 100000)
@@ -3161,7 +3221,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             if (h->no_prefilter) run_len = -run_len;
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
                 h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], R, h->d_meta(), h->prm.num_save,
-                h->d_cands(0), cand_cap, run_len);
+                static_cast<uint4 *>(h->b_c16.p), cand_cap, run_len, fill_ref);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_LEAF]++;
         }
@@ -3192,7 +3252,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             CK(cudaEventRecord(h->evk[es][3], h->stream));
             // algorithmic bytes of the launch: the count word of every item, the item itself where it was
             // evaluated, the candidate records written
-            st.kernel_bytes[LICHEE_K_LEAF] += B * 4ll + (B - (long long)h->h_meta->n_bounded) * (long long)h->stride + m * (long long)sizeof(Cand);
+            st.kernel_bytes[LICHEE_K_LEAF] += B * 4ll + (B - (long long)h->h_meta->n_bounded) * (long long)h->stride + m * 16ll;
             st.num_evaluated += (long long)h->h_meta->n_eval;
             st.num_bounded_items += (long long)h->h_meta->n_bounded;
             st.num_leaf_items += B;
@@ -3201,11 +3261,14 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
             }
             if (m > 0) {
-                if (ensure(h, h->b_key0, 8 * (size_t)m) != LICHEE_OK || ensure(h, h->b_key1, 8 * (size_t)m) != LICHEE_OK) return LICHEE_ERR_CUDA;
-                seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(h->d_cands(0), m, h->head[lv], lmask,
+                if (ensure(h, h->b_key0, 8 * (size_t)m) != LICHEE_OK || ensure(h, h->b_key1, 8 * (size_t)m) != LICHEE_OK ||
+                    ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)m) != LICHEE_OK)
+                    return LICHEE_ERR_CUDA;
+                seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(static_cast<const uint4 *>(h->b_c16.p), h->d_cands(0), m, h->head[lv], lmask,
                                                                              h->d_off(), seq_base, h->prm.max_num_trees,
                                                                              static_cast<unsigned long long *>(h->b_key0.p),
-                                                                             static_cast<unsigned long long *>(h->b_key1.p));
+                                                                             static_cast<unsigned long long *>(h->b_key1.p), h->d_meta(),
+                                                                             h->prm.num_save, R);
                 CK(cudaGetLastError());
                 st.num_launches++;
                 int src = 0;
@@ -3253,6 +3316,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                         static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p), static_cast<double *>(h->b_lbound.p), h->d_scan());
                     CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
                     fill_pending = true;                      // read at the next last-level chunk
+                    fill_ref = items;
                     fill_items = total_fit;
                     fill_parents = n_fit;
                 } else {
@@ -3276,7 +3340,10 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * f : f;
             seen[lv] = true;
         }
-        if (h->head[lv] == h->tail[lv]) h->head[lv] = h->tail[lv] = 0;
+        if (h->head[lv] == h->tail[lv]) {
+            h->head[lv] = h->tail[lv] = 0;
+            if (leaf) fill_ref = nullptr;
+        }
         if (seq_base >= h->prm.max_num_trees) { st.status |= LICHEE_STATUS_TREE_CAP; break; }
         if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
     }
@@ -3499,7 +3566,7 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_slab);
     give_back(h, h->b_sched);
     give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag); give_back(h, h->b_bound);
-    give_back(h, h->b_lmask); give_back(h, h->b_lcnt); give_back(h, h->b_lbound);
+    give_back(h, h->b_lmask); give_back(h, h->b_lcnt); give_back(h, h->b_lbound); give_back(h, h->b_c16);
     give_back(h, h->b_rblob); give_back(h, h->b_rrec);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     {
