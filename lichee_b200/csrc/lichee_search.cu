@@ -1005,6 +1005,65 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
     unsigned wb_prev = 0;
     const bool has_x = level >= 1;
     const int wl3 = has_x ? item_byte(level - 1, wstride) >> 2 : 0, sh3 = has_x ? 8 * (item_byte(level - 1, wstride) & 3) : 0;
+    // Reference state of the block.  A run used to start with a full evaluation of its first item (every present
+    // row: a third of the kernel's instructions at ~20 items per run).  The items of a block are neighbours in the
+    // canonical order and share all but their last few bytes, so the block evaluates its FIRST item together -- every
+    // warp a 16th of the rows -- and each run starts from that state, redoing only the rows named by the bytes in
+    // which its first item differs (or everything, when those are many).  Same arithmetic per row.
+    bool have_state = false;
+    {
+        const long long ref_it = (long long)blockIdx.x * kWarpsPerBlock * run_len;
+        if (has_x && ref_it < n_items) {
+            __shared__ double eref_s[kMaxN];
+            __shared__ unsigned bvref_s[4], bbref_s[4], buref_s[4];
+            const int wid = threadIdx.x >> 5;
+            if (threadIdx.x < 4) {
+                const int t = threadIdx.x;
+                bvref_s[t] = t == 0 ? sokv.x : t == 1 ? sokv.y : t == 2 ? sokv.z : sokv.w;
+                bbref_s[t] = t == 0 ? sboth.x : t == 1 ? sboth.y : t == 2 ? sboth.z : sboth.w;
+                buref_s[t] = t == 0 ? soku.x : t == 1 ? soku.y : t == 2 ? soku.z : soku.w;
+            }
+            unsigned wr = lane < wstride ? __ldg(items + ref_it * wstride + lane) : 0xffffffffu;
+            if (lane == wl3) wr |= 0xffu << sh3;
+            parent_presence(wr, rmax, um0);
+            __syncthreads();
+            int rank = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                unsigned rows = prune ? um0[g] : um0[g] & (candq[g] | candq2[g]);
+                while (rows) {
+                    const int bq = __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    if ((rank++ & (kWarpsPerBlock - 1)) != wid) continue;
+                    const unsigned q = g * 32 + bq;
+                    const bool is_cv = ((candq[g] >> bq) & 1u) != 0, is_cu = ((candq2[g] >> bq) & 1u) != 0;
+                    double Eq = 0.0;
+                    const unsigned r = dual_row<SPL>(wr, q, rmax, wstride, vaf_s, SP, lane, xv0, xv1, xu0, xu1, net.margin, valid0,
+                                                     valid1, is_cv, is_cu, prune, Eq);
+                    if (lane == 0) {
+                        eref_s[q] = Eq;
+                        if (is_cv) {
+                            const unsigned iv = cidx_s[q], bit = 1u << (iv & 31);
+                            if (r & 1u) atomicOr(&bvref_s[iv >> 5], bit); else atomicAnd(&bvref_s[iv >> 5], ~bit);
+                            if (r & 2u) atomicOr(&bbref_s[iv >> 5], bit); else atomicAnd(&bbref_s[iv >> 5], ~bit);
+                        }
+                        if (is_cu) {
+                            const unsigned iu = cidx2_s[q], bit = 1u << (iu & 31);
+                            if (r & 4u) atomicOr(&buref_s[iu >> 5], bit); else atomicAnd(&buref_s[iu >> 5], ~bit);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                bv0[g] = bvref_s[g]; bb0[g] = bbref_s[g]; bu0[g] = buref_s[g];
+                E0[g] = (prune && ((um0[g] >> lane) & 1u)) ? eref_s[g * 32 + lane] : 0.0;
+            }
+            wb_prev = wr;
+            have_state = true;
+        }
+    }
     for (long long run0 = warp0 * run_len; run0 < n_items; run0 += nwarps * run_len) {
         const long long run1 = run0 + run_len < n_items ? run0 + run_len : n_items;
         unsigned w_next = lane < wstride ? __ldg(items + run0 * wstride + lane) : 0xffffffffu;
@@ -1012,7 +1071,8 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
             const unsigned w = w_next;
             if (it + 1 < run1) w_next = lane < wstride ? __ldg(items + (it + 1) * wstride + lane) : 0xffffffffu;
             const unsigned wb = (has_x && lane == wl3) ? (w | (0xffu << sh3)) : w;     // the item with x taken out
-            bool fresh = it == run0;
+            bool fresh = !have_state;
+            have_state = true;
             unsigned todo[4] = {0, 0, 0, 0};
             if (!fresh) {
                 const unsigned diff = wb ^ wb_prev;
