@@ -2041,14 +2041,24 @@ radix12_pass(const unsigned long long *__restrict__ key0, const unsigned long lo
     const unsigned dmask = (1u << width) - 1u;
     for (int i = threadIdx.x; i < 4096; i += 256) h[i] = 0;
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long k0 = key0[i];
-        if (k0 == ~0ull) continue;                       // empty slot
-        if (word == 0) {
-            if (hi >= 64 || (k0 >> hi) == (p0 >> hi)) atomicAdd(&h[(unsigned)(k0 >> shift) & dmask], 1u);
-        } else if (k0 == p0) {
-            const unsigned long long k1 = key1[i];
-            if (hi >= 64 || (k1 >> hi) == (p1 >> hi)) atomicAdd(&h[(unsigned)(k1 >> shift) & dmask], 1u);
+    // four keys per thread and iteration, loaded together (the loop is bound by the latency of its loads)
+    for (long long base = (long long)blockIdx.x * 1024; base < m; base += (long long)gridDim.x * 1024) {
+        unsigned long long k0v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long i = base + j * 256 + threadIdx.x;
+            k0v[j] = i < m ? key0[i] : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned long long k0 = k0v[j];
+            if (k0 == ~0ull) continue;                   // empty slot
+            if (word == 0) {
+                if (hi >= 64 || (k0 >> hi) == (p0 >> hi)) atomicAdd(&h[(unsigned)(k0 >> shift) & dmask], 1u);
+            } else if (k0 == p0) {
+                const unsigned long long k1 = key1[base + j * 256 + threadIdx.x];
+                if (hi >= 64 || (k1 >> hi) == (p1 >> hi)) atomicAdd(&h[(unsigned)(k1 >> shift) & dmask], 1u);
+            }
         }
     }
     __syncthreads();
@@ -2063,10 +2073,33 @@ radix12_pass(const unsigned long long *__restrict__ key0, const unsigned long lo
     for (int j = 0; j < 16; j++) { const unsigned v = *(volatile unsigned *)&st->hist[threadIdx.x * 16 + j]; h[threadIdx.x * 16 + j] = v; mine += v; }
     part[threadIdx.x] = mine;
     __syncthreads();
+    __shared__ int g_s;
+    __shared__ unsigned long long run_s;
+    if (threadIdx.x < 32) {
+        // warp 0: the group of 16 bins in which the running count reaches k (8 partial sums per lane, then a shuffle scan)
+        const unsigned long long k = st->k;
+        unsigned long long v[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { v[j] = part[threadIdx.x * 8 + j]; tot += v[j]; }
+        unsigned long long inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(kFull, inc, d);
+            if ((int)threadIdx.x >= d) inc += t;
+        }
+        const unsigned reach = __ballot_sync(kFull, inc >= k);
+        if (reach == 0) { if (threadIdx.x == 0) { g_s = 256; run_s = 0; } }
+        else if ((int)threadIdx.x == __ffs(reach) - 1) {
+            unsigned long long run = inc - tot;
+            int j = 0;
+            for (; j < 8; j++) { if (run + v[j] >= k) break; run += v[j]; }
+            g_s = threadIdx.x * 8 + j; run_s = run;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long k = st->k, run = 0;
-        int g = 0;
-        for (; g < 256; g++) { if (run + part[g] >= k) break; run += part[g]; }
+        unsigned long long k = st->k, run = run_s;
+        const int g = g_s;
         if (g == 256) {                                 // fewer than k candidates in the bucket: keep everything
             st->done = 1; st->thresh[0] = st->thresh[1] = ~0ull;
         } else {
@@ -2102,12 +2135,22 @@ radix12_compact(const Cand *__restrict__ cands, const unsigned long long *__rest
                 const unsigned long long *__restrict__ key1, long long m, Radix12State *st, Cand *__restrict__ out, long long out_cap) {
     if (!st->done) return;
     const unsigned long long t0 = st->thresh[0], t1 = st->thresh[1];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long k0 = key0[i];
-        if (k0 == ~0ull) continue;
-        if (k0 < t0 || (k0 == t0 && key1[i] <= t1)) {
-            const unsigned long long slot = atomicAdd(&st->kept, 1ull);
-            if ((long long)slot < out_cap) out[slot] = cands[i];       // only the survivors' records are read
+    for (long long base = (long long)blockIdx.x * 1024; base < m; base += (long long)gridDim.x * 1024) {
+        unsigned long long k0v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long i = base + j * 256 + threadIdx.x;
+            k0v[j] = i < m ? key0[i] : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long i = base + j * 256 + threadIdx.x;
+            const unsigned long long k0 = k0v[j];
+            if (k0 == ~0ull) continue;
+            if (k0 < t0 || (k0 == t0 && key1[i] <= t1)) {
+                const unsigned long long slot = atomicAdd(&st->kept, 1ull);
+                if ((long long)slot < out_cap) out[slot] = cands[i];   // only the survivors' records are read
+            }
         }
     }
 }
@@ -2958,7 +3001,7 @@ int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq
         ensure(h, h->b_cands[1], sizeof(Cand) * (size_t)kSelTile) != LICHEE_OK)
         return LICHEE_ERR_CUDA;
     Radix12State *st = static_cast<Radix12State *>(h->b_radix12.p);
-    const int grid = (int)std::min<long long>((m + 255) / 256, 148 * 8);
+    const int grid = (int)std::min<long long>((m + 1023) / 1024, 148 * 8);
     radix12_init<<<1, 256, 0, h->stream>>>(st, h->d_meta(), (unsigned long long)h->prm.num_save, (unsigned long long)seq_lo,
                                            (unsigned long long)seq_hi);
     h->stats.num_launches++;
