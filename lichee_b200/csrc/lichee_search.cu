@@ -1848,20 +1848,29 @@ select_kernel(TopMeta *meta, int num_save, const Cand *__restrict__ cands, long 
     // gather parent bytes of the survivors
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int wl = item_byte(last_level, wstride) >> 2, sh = 8 * (item_byte(last_level, wstride) & 3);
-    for (unsigned t = wid; t < newc; t += kSelThreads / 32) {
-        const Cand c = res[t];
+    // (four trees per warp and iteration, their words requested together: the loop is bound by the latency of the loads)
+    for (unsigned t0 = wid * 4; t0 < newc; t0 += kSelThreads / 32 * 4) {
         for (int j = lane; j < wstride; j += 32) {      // (reference-order records are 2 x stride bytes: up to 64 words)
-            unsigned w;
-            if (c.origin & 0x80000000u) {
-                w = tree_cur[(size_t)(c.origin & 0x7fffffffu) * wstride + j];
-            } else if (external_records) {
-                const unsigned *src = reinterpret_cast<const unsigned *>(records + (size_t)c.origin * record_bytes + 24);
-                w = src[j];
-            } else {
-                w = leaf_items[(size_t)c.origin * wstride + j];
-                if (j == wl) w = (w & ~(0xffu << sh)) | (c.pstar << sh);
+            unsigned w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned t = t0 + u;
+                w[u] = 0;
+                if (t >= newc) continue;
+                const unsigned origin = res[t].origin, pstar = res[t].pstar;
+                if (origin & 0x80000000u) {
+                    w[u] = tree_cur[(size_t)(origin & 0x7fffffffu) * wstride + j];
+                } else if (external_records) {
+                    const unsigned *src = reinterpret_cast<const unsigned *>(records + (size_t)origin * record_bytes + 24);
+                    w[u] = src[j];
+                } else {
+                    w[u] = leaf_items[(size_t)origin * wstride + j];
+                    if (j == wl) w[u] = (w[u] & ~(0xffu << sh)) | (pstar << sh);
+                }
             }
-            tree_next[(size_t)t * wstride + j] = w;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (t0 + u < newc) tree_next[(size_t)(t0 + u) * wstride + j] = w[u];
         }
     }
     for (int t = threadIdx.x; t < (int)newc; t += kSelThreads) top_next[t] = res[t];
