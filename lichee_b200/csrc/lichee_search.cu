@@ -989,7 +989,9 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
     bool full;
     double tau;
     const double tmax = admit_bound(meta, num_save, full, tau);
-    const bool prune = net.prune != 0 && full;
+    // (the bound is computed whenever the network allows it, also while the list is still filling up: this launch may
+    //  run ahead of the selection that fills it, and emit2_kernel compares the bound with the threshold of ITS moment)
+    const bool prune = net.prune != 0;
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
 
@@ -1164,7 +1166,7 @@ check2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items,
             double tb = 0.0;
             if (prune) {
                 tb = butterfly_sum(__dadd_rn(__dadd_rn(E[0], E[1]), __dadd_rn(E[2], E[3])));
-                flag = tb > tmax ? 1u : 0u;
+                flag = (full && tb > tmax) ? 1u : 0u;
             }
             if (lane == 0) {
                 bound_out[it] = tb;                      // kept with the children: a later, tighter threshold re-tests it for free
@@ -1187,7 +1189,8 @@ __global__ void __launch_bounds__(kThreads)
 emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, const uint4 *__restrict__ mask,
              const unsigned *__restrict__ off, const uint4 *__restrict__ both, const uint4 *__restrict__ masku,
              const unsigned *__restrict__ flag, const double *__restrict__ bound, unsigned *__restrict__ out,
-             uint4 *__restrict__ lmask_out, unsigned *__restrict__ lcnt_out, double *__restrict__ lbound_out, ScanOut *so) {
+             uint4 *__restrict__ lmask_out, unsigned *__restrict__ lcnt_out, double *__restrict__ lbound_out, ScanOut *so,
+             const TopMeta *meta, int num_save) {
     __shared__ uint8_t cand_s[kMaxN], cidx2_s[kMaxN];
     __shared__ unsigned candq2_s[4];
     const int level = net.L - 2;
@@ -1207,17 +1210,26 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
     const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
     unsigned long long my_trees = 0, my_live = 0;       // per lane, reduced at the end
+    // The flag was set by check2_kernel against the threshold of ITS launch -- which may have run ahead, beside the
+    // selection of the previous fill (run_search, prefetch); the bound came with it, so it is compared once more with
+    // what the list admits now: a base the newer threshold dismisses costs count words only and no last-level launch.
+    bool full;
+    double tau;
+    const double tmax = admit_bound(meta, num_save, full, tau);
+    const bool prune = net.prune != 0 && full;
     // the next base's words are requested while this one is written (the loop is bound by their latency)
     uint4 m4n = make_uint4(0, 0, 0, 0), mbn = m4n, mun = m4n;
     unsigned fln = 0, offn = 0;
-    if (warp0 < n_items) { m4n = mask[warp0]; mbn = both[warp0]; mun = masku[warp0]; fln = flag[warp0]; offn = off[warp0]; }
+    double tbn = 0.0;
+    if (warp0 < n_items) { m4n = mask[warp0]; mbn = both[warp0]; mun = masku[warp0]; fln = flag[warp0]; offn = off[warp0]; tbn = bound[warp0]; }
     for (long long it = warp0; it < n_items; it += nwarps) {
         const uint4 m4 = m4n, mb = mbn, mu = mun;
-        const unsigned fl = fln ? kBounded : 0u;
+        const double tb = tbn;
+        const unsigned fl = (fln || (prune && tb > tmax)) ? kBounded : 0u;
         long long dst = (long long)offn;
         if (it + nwarps < n_items) {
             const long long nx = it + nwarps;
-            m4n = mask[nx]; mbn = both[nx]; mun = masku[nx]; fln = flag[nx]; offn = off[nx];
+            m4n = mask[nx]; mbn = both[nx]; mun = masku[nx]; fln = flag[nx]; offn = off[nx]; tbn = bound[nx];
         }
         if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
         const unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
@@ -1242,7 +1254,6 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
             continue;
         }
         const unsigned w = lane < wstride ? __ldg(items + it * wstride + lane) : 0xffffffffu;
-        const double tb = bound[it];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             unsigned b = mw[g];
@@ -2781,6 +2792,8 @@ DevicePool g_pool;
 struct DevCtx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk[2][6] = {};
+    cudaStream_t stream2 = nullptr;      // check2_kernel of the NEXT chunk, beside the last level of the current fill
+    cudaEvent_t evp[3] = {};             // its start / end (timing) and completion (what the main stream waits for)
     void *pinned = nullptr;
     void *pinned_big = nullptr;          // initial replay state | fused result block (device-visible)
 };
@@ -2826,6 +2839,10 @@ struct lichee_search {
     long long cand_cap = 0;                  // upper bound on candidates one last-level launch may append
     DevBuf b_mask, b_cnt, b_off, b_tile, b_small, b_radix, b_radix12, b_key0, b_key1, b_cands[2], b_top[2], b_tree[2];
     DevBuf b_mask2, b_mask3, b_flag, b_bound; // level L-2 chunks: "v and u" mask, "u without v" mask, bounded flag, bound value
+    DevBuf b_pf[6];                          // the same six arrays (mask, count, mask2, mask3, flag, bound), second set: consecutive chunks alternate
+    cudaStream_t stream2 = nullptr;          // check2_kernel of the next level L-2 chunk runs here, beside the last level of the current fill
+    cudaEvent_t evp[3] = {};
+    bool no_prefetch = false;                // LICHEE_NO_PREFETCH=1: every kernel on the one stream, in program order
     DevBuf b_lmask, b_lcnt, b_lbound;        // last level, parallel to its item buffer: pass mask, count | flags, bound of the base
     DevBuf b_c16;                            // 16-byte candidates of the running last-level launch (leaf_kernel -> seq_fixup_kernel)
     uint4 sok_last{};                        // static pass mask of the last node (n == 2: the only item's mask)
@@ -3201,6 +3218,53 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
     long long fill_items = 0, fill_live = 0, fill_trees = 0, fill_parents = 0;
     bool fill_pending = false;               // emit2's counters are still on their way to the host
     const unsigned *fill_ref = nullptr;      // an item of the level above from the chunk the current fill came from (leaf_kernel's reference base)
+    // check2_kernel of the NEXT level L-2 chunk is launched on the second stream as soon as the children of the current
+    // one have been emitted: it runs beside the last level of the current fill, whose selection kernels are single
+    // blocks and whose read-backs leave the GPU idle.  The two sets of result arrays alternate between consecutive
+    // chunks; its flags are set against the threshold of the moment and refreshed by emit2_kernel (the bound comes along).
+    struct { bool valid = false; long long head = 0, B = 0; int set = 0; } pf;
+    int c2set = 0;                           // result arrays of the level L-2 chunk in hand
+    auto c2buf = [&](int set, int which) -> DevBuf & {
+        if (set) return h->b_pf[which];
+        return which == 0 ? h->b_mask : which == 1 ? h->b_cnt : which == 2 ? h->b_mask2 : which == 3 ? h->b_mask3 : which == 4 ? h->b_flag : h->b_bound;
+    };
+    auto launch_check2 = [&](cudaStream_t strm, int set, const unsigned *c2items, long long nb) -> int {
+        static const size_t unit[6] = {sizeof(uint4), 4, sizeof(uint4), sizeof(uint4), 4, 8};
+        for (int w = 0; w < 6; w++)
+            if (ensure(h, c2buf(set, w), unit[w] * (size_t)nb) != LICHEE_OK) return LICHEE_ERR_CUDA;
+        // one run per warp, sized so that the grid is one full wave of two blocks per SM (a run starts from the
+        // block's reference state: runs shorter than 8 items do not pay)
+        const long long slots = 148ll * 2 * kWarpsPerBlock;
+        const int run_len = (int)std::min<long long>(64, std::max<long long>(8, (nb + slots - 1) / slots));
+        const int grid = (int)std::min<long long>(148 * 2, (nb + (long long)run_len * kWarpsPerBlock - 1) / ((long long)run_len * kWarpsPerBlock));
+        check2_kernel<SPL><<<grid, kThreads, h->smem, strm>>>(
+            h->net, c2items, nb, static_cast<uint4 *>(c2buf(set, 0).p), static_cast<unsigned *>(c2buf(set, 1).p),
+            static_cast<uint4 *>(c2buf(set, 2).p), static_cast<uint4 *>(c2buf(set, 3).p), static_cast<unsigned *>(c2buf(set, 4).p),
+            static_cast<double *>(c2buf(set, 5).p), h->d_meta(), h->prm.num_save, run_len);
+        CK(cudaGetLastError());
+        st.num_launches++;
+        st.kernel_launches[LICHEE_K_CHECK]++;
+        st.kernel_bytes[LICHEE_K_CHECK] += nb * (long long)(h->stride + 64);
+        return LICHEE_OK;
+    };
+    // chunk of a level below the last one: what is pending, cut to what the remaining tree budget can use and to
+    // what the next level is expected to hold
+    auto chunk_rule = [&](int lv, long long pending, bool leaf) -> long long {
+        long long B = std::min(pending, h->chunk_max);
+        if (sliced) {
+            // trees still wanted / trees expected below one item of this level
+            double yield = 1.0;
+            for (int l = lv; l < L; l++)   // unseen levels: assume every candidate passes, so the first descent stays narrow
+                yield = std::min(1e30, yield * std::max(seen[l] ? fan[l] : (double)h->cands[l].size(), 1e-3));
+            const double want = 1.25 * (double)(h->prm.max_num_trees - seq_base) / yield + 8.0;
+            if ((double)B > want) B = (long long)want;
+        }
+        if (!leaf) {
+            const long long guess = (long long)(0.8 * (double)h->cap / std::max(1.0, fan[lv]));
+            B = std::min(B, std::max(1024ll, guess));
+        }
+        return B < 1 ? 1 : B;
+    };
     for (;;) {
         int lv = -1;
         if (!sliced) {
@@ -3232,20 +3296,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         const long long pending = h->tail[lv] - h->head[lv];
         const bool leaf = lv == L - 1;
         const long long kcand = (long long)h->cands[lv].size();
-        long long B = std::min(pending, h->chunk_max);
-        if (sliced) {
-            // trees still wanted / trees expected below one item of this level
-            double yield = 1.0;
-            for (int l = lv; l < L; l++)   // unseen levels: assume every candidate passes, so the first descent stays narrow
-                yield = std::min(1e30, yield * std::max(seen[l] ? fan[l] : (double)h->cands[l].size(), 1e-3));
-            const double want = 1.25 * (double)(h->prm.max_num_trees - seq_base) / yield + 8.0;
-            if ((double)B > want) B = (long long)want;
-        }
-        if (!leaf) {
-            const long long guess = (long long)(0.8 * (double)h->cap / std::max(1.0, fan[lv]));
-            B = std::min(B, std::max(1024ll, guess));
-        }
-        if (B < 1) B = 1;
+        long long B = chunk_rule(lv, pending, leaf);
         if (leaf && fill_pending) {
             CK(cudaStreamSynchronize(h->stream));
             fill_pending = false;
@@ -3282,10 +3333,16 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         }
         const unsigned *items = h->level(lv) + (size_t)h->head[lv] * (h->stride >> 2);
         const bool dual = lv == L - 2;                       // the level whose children are the last-level items
-        if (dual && (ensure(h, h->b_mask2, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_mask3, sizeof(uint4) * (size_t)B) != LICHEE_OK ||
-                     ensure(h, h->b_flag, 4 * (size_t)B) != LICHEE_OK || ensure(h, h->b_bound, 8 * (size_t)B) != LICHEE_OK))
-            return LICHEE_ERR_CUDA;
-        if (ensure(h, h->b_mask, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_cnt, 4 * (size_t)B) != LICHEE_OK ||
+        // the chunk may have been checked already, beside the last level of the fill before it
+        bool prefetched = false;
+        if (pf.valid && !leaf) {
+            if (dual && pf.head == h->head[lv]) { prefetched = true; B = pf.B; c2set = pf.set; }
+            else CK(cudaStreamSynchronize(h->stream2));      // (not reached: the chunk after a fill is the next one of its level)
+            pf.valid = false;
+        } else if (dual) {
+            c2set = 0;
+        }
+        if ((!dual && !leaf && (ensure(h, h->b_mask, sizeof(uint4) * (size_t)B) != LICHEE_OK || ensure(h, h->b_cnt, 4 * (size_t)B) != LICHEE_OK)) ||
             ensure(h, h->b_off, 4 * (size_t)B) != LICHEE_OK ||
             ensure(h, h->b_tile, 8 * (size_t)(B / kScanTile + 2)) != LICHEE_OK)
             return LICHEE_ERR_CUDA;
@@ -3297,17 +3354,19 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         const unsigned *lcnt = static_cast<const unsigned *>(h->b_lcnt.p) + (leaf ? h->head[lv] : 0);
         const uint4 *lmask = static_cast<const uint4 *>(h->b_lmask.p) + (leaf ? h->head[lv] : 0);
         if (dual) {
-            // one run per warp, sized so that the grid is one full wave of two blocks per SM (the first item of a
-            // run is evaluated in full, every present row with its excess: runs shorter than 8 items do not pay)
-            const long long slots = 148ll * 2 * kWarpsPerBlock;
-            const int run_len = (int)std::min<long long>(64, std::max<long long>(8, (B + slots - 1) / slots));
-            const int grid = (int)std::min<long long>(148 * 2, (B + (long long)run_len * kWarpsPerBlock - 1) / ((long long)run_len * kWarpsPerBlock));
-            check2_kernel<SPL><<<grid, kThreads, h->smem, h->stream>>>(
-                h->net, items, B, h->d_mask(), h->d_cnt(), static_cast<uint4 *>(h->b_mask2.p), static_cast<uint4 *>(h->b_mask3.p),
-                static_cast<unsigned *>(h->b_flag.p), static_cast<double *>(h->b_bound.p), h->d_meta(), h->prm.num_save, run_len);
-            CK(cudaGetLastError());
-            st.kernel_launches[LICHEE_K_CHECK]++;
-            st.kernel_bytes[LICHEE_K_CHECK] += B * (long long)(h->stride + 64);
+            if (prefetched) {
+                // its time on the second stream goes to the check column; the main stream only waits for its end
+                CK(cudaStreamWaitEvent(h->stream, h->evp[2], 0));
+                CK(cudaEventSynchronize(h->evp[2]));
+                float pms = 0;
+                CK(cudaEventElapsedTime(&pms, h->evp[0], h->evp[1]));
+                st.kernel_ms[LICHEE_K_CHECK] += pms;
+                st.num_launches--;                           // (counted again below with the chunk)
+            } else if (launch_check2(h->stream, c2set, items, B) != LICHEE_OK) {
+                return LICHEE_ERR_CUDA;
+            } else {
+                st.num_launches--;
+            }
         } else if (!leaf) {
             if (launch_check<SPL>(h, lv, items, B) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_launches[LICHEE_K_CHECK]++;
@@ -3339,7 +3398,8 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         }
         CK(cudaEventRecord(h->evk[es][1], h->stream));
         if (!leaf) {
-            if (launch_scan(h, h->d_cnt(), B, (unsigned long long)h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
+            const unsigned *cnt_in = dual ? static_cast<const unsigned *>(c2buf(c2set, 1).p) : h->d_cnt();
+            if (launch_scan(h, cnt_in, B, (unsigned long long)h->cap) != LICHEE_OK) return LICHEE_ERR_CUDA;
             st.kernel_bytes[LICHEE_K_SCAN] += B * 12ll;
         }
         CK(cudaEventRecord(h->evk[es][2], h->stream));
@@ -3410,6 +3470,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             CK(cudaStreamSynchronize(h->stream));
             const long long n_fit = (long long)(h->h_scan->fit >> 32);
             const long long total_fit = (long long)(h->h_scan->fit & 0xffffffffull);
+            if (getenv("LICHEE_DEBUG") && lv >= L - 3) fprintf(stderr, "level %d chunk B=%lld fit=%lld children=%lld prefetched=%d fan=%.2f pending=%lld\n", lv, B, n_fit, total_fit, prefetched ? 1 : 0, fan[lv], pending);
             if (n_fit == 0) {
                 set_err("level_capacity %lld too small for one item's children", h->cap);
                 return LICHEE_ERR_INVALID;
@@ -3422,10 +3483,11 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                         return LICHEE_ERR_CUDA;
                     CK(cudaMemsetAsync(&h->d_scan()->live, 0, 2 * sizeof(unsigned long long), h->stream));
                     emit2_kernel<<<grid_for(n_fit), kThreads, 0, h->stream>>>(
-                        h->net, items, n_fit, h->d_mask(), h->d_off(), static_cast<const uint4 *>(h->b_mask2.p),
-                        static_cast<const uint4 *>(h->b_mask3.p), static_cast<const unsigned *>(h->b_flag.p),
-                        static_cast<const double *>(h->b_bound.p), h->level(lv + 1),
-                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p), static_cast<double *>(h->b_lbound.p), h->d_scan());
+                        h->net, items, n_fit, static_cast<const uint4 *>(c2buf(c2set, 0).p), h->d_off(), static_cast<const uint4 *>(c2buf(c2set, 2).p),
+                        static_cast<const uint4 *>(c2buf(c2set, 3).p), static_cast<const unsigned *>(c2buf(c2set, 4).p),
+                        static_cast<const double *>(c2buf(c2set, 5).p), h->level(lv + 1),
+                        static_cast<uint4 *>(h->b_lmask.p), static_cast<unsigned *>(h->b_lcnt.p), static_cast<double *>(h->b_lbound.p), h->d_scan(),
+                        h->d_meta(), h->prm.num_save);
                     CK(cudaMemcpyAsync(h->h_scan, h->d_scan(), sizeof(ScanOut), cudaMemcpyDeviceToHost, h->stream));
                     fill_pending = true;                      // read at the next last-level chunk
                     fill_ref = items;
@@ -3451,6 +3513,15 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             const double f = (double)total_fit / (double)n_fit;
             fan[lv] = seen[lv] ? 0.5 * fan[lv] + 0.5 * f : f;
             seen[lv] = true;
+            if (dual && sliced && !h->no_prefetch && total_fit > 0 && h->tail[lv] > h->head[lv]) {
+                // the next chunk of this level, checked beside the fill that was just emitted
+                const long long nb = chunk_rule(lv, h->tail[lv] - h->head[lv], false);
+                pf.valid = true; pf.head = h->head[lv]; pf.B = nb; pf.set = c2set ^ 1;
+                CK(cudaEventRecord(h->evp[0], h->stream2));
+                if (launch_check2(h->stream2, pf.set, h->level(lv) + (size_t)pf.head * (h->stride >> 2), nb) != LICHEE_OK) return LICHEE_ERR_CUDA;
+                CK(cudaEventRecord(h->evp[1], h->stream2));
+                CK(cudaEventRecord(h->evp[2], h->stream2));
+            }
         }
         if (h->head[lv] == h->tail[lv]) {
             h->head[lv] = h->tail[lv] = 0;
@@ -3459,6 +3530,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
         if (seq_base >= h->prm.max_num_trees) { st.status |= LICHEE_STATUS_TREE_CAP; break; }
         if (st.num_grow_calls >= h->prm.max_num_grow_calls) { st.status |= LICHEE_STATUS_GROW_CAP; break; }
     }
+    if (pf.valid) CK(cudaStreamSynchronize(h->stream2));     // a chunk checked ahead that a cap made unnecessary
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (harvest_events(h, 0) != LICHEE_OK || harvest_events(h, 1) != LICHEE_OK) return LICHEE_ERR_CUDA;
@@ -3648,7 +3720,9 @@ int lichee_release_cached_memory(void) {
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) if (c.evk[a][b]) cudaEventDestroy(c.evk[a][b]);
+        for (int a = 0; a < 3; a++) if (c.evp[a]) cudaEventDestroy(c.evp[a]);
         if (c.stream) cudaStreamDestroy(c.stream);
+        if (c.stream2) cudaStreamDestroy(c.stream2);
     }
     g_ctx.free_list.clear();
     return LICHEE_OK;
@@ -3668,6 +3742,7 @@ int lichee_search_destroy(lichee_search *h) {
     if (h->stream) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
+        if (h->stream2) cudaStreamSynchronize(h->stream2);
     }
     give_back(h, h->b_net);
     for (DevBuf &b : h->b_level) give_back(h, b);
@@ -3678,14 +3753,17 @@ int lichee_search_destroy(lichee_search *h) {
     give_back(h, h->b_slab);
     give_back(h, h->b_sched);
     give_back(h, h->b_mask2); give_back(h, h->b_mask3); give_back(h, h->b_flag); give_back(h, h->b_bound);
+    for (DevBuf &b : h->b_pf) give_back(h, b);
     give_back(h, h->b_lmask); give_back(h, h->b_lcnt); give_back(h, h->b_lbound); give_back(h, h->b_c16);
     give_back(h, h->b_rblob); give_back(h, h->b_rrec);
     for (int i = 0; i < 2; i++) { give_back(h, h->b_cands[i]); give_back(h, h->b_top[i]); give_back(h, h->b_tree[i]); }
     {
         DevCtx c;
         c.stream = h->stream; c.ev0 = h->ev0; c.ev1 = h->ev1; c.pinned = h->h_scan; c.pinned_big = h->h_big;
-        bool whole = c.stream && c.ev0 && c.ev1 && c.pinned && c.pinned_big;
+        c.stream2 = h->stream2;
+        bool whole = c.stream && c.stream2 && c.ev0 && c.ev1 && c.pinned && c.pinned_big;
         for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) { c.evk[x][y] = h->evk[x][y]; whole = whole && c.evk[x][y]; }
+        for (int x = 0; x < 3; x++) { c.evp[x] = h->evp[x]; whole = whole && c.evp[x]; }
         if (whole) {
             g_ctx.put(h->device, c);
         } else {
@@ -3695,7 +3773,9 @@ int lichee_search_destroy(lichee_search *h) {
             if (c.ev0) cudaEventDestroy(c.ev0);
             if (c.ev1) cudaEventDestroy(c.ev1);
             for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) if (c.evk[x][y]) cudaEventDestroy(c.evk[x][y]);
+            for (int x = 0; x < 3; x++) if (c.evp[x]) cudaEventDestroy(c.evp[x]);
             if (c.stream) cudaStreamDestroy(c.stream);
+            if (c.stream2) cudaStreamDestroy(c.stream2);
         }
     }
     delete h;
@@ -3793,8 +3873,15 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
             h->stream = c.stream; h->ev0 = c.ev0; h->ev1 = c.ev1; h->h_scan = static_cast<ScanOut *>(c.pinned);
             h->h_big = static_cast<unsigned char *>(c.pinned_big);
             for (int x = 0; x < 2; x++) for (int y = 0; y < 6; y++) h->evk[x][y] = c.evk[x][y];
+            h->stream2 = c.stream2;
+            for (int x = 0; x < 3; x++) h->evp[x] = c.evp[x];
         } else {
-            CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            // the second stream only fills what the main one leaves idle: lowest priority against highest
+            int prio_lo = 0, prio_hi = 0;
+            CKD(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CKD(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+            CKD(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo));
+            for (int a = 0; a < 3; a++) CKD(cudaEventCreate(&h->evp[a]));
             CKD(cudaEventCreate(&h->ev0)); CKD(cudaEventCreate(&h->ev1));
             for (int a = 0; a < 2; a++) for (int b = 0; b < 6; b++) CKD(cudaEventCreate(&h->evk[a][b]));
             CKD(cudaMallocHost(&h->h_scan, sizeof(ScanOut) + sizeof(TopMeta) + sizeof(Sched) + sizeof(ReplayOut)));
@@ -3908,6 +3995,7 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->h_rout = reinterpret_cast<ReplayOut *>(h->h_sched + 1);
     h->narrow = getenv("LICHEE_NO_NARROW") == nullptr;
     h->no_prefilter = getenv("LICHEE_NO_PREFILTER") != nullptr;
+    h->no_prefetch = getenv("LICHEE_NO_PREFETCH") != nullptr;
     h->net.vaf = reinterpret_cast<const double *>(nb);
     h->net.static_ok = reinterpret_cast<const uint4 *>(nb + o_sok);
     h->net.leaf_static = reinterpret_cast<const double *>(nb + o_ls);

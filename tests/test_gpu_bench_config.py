@@ -4,8 +4,8 @@ tests/golden/canonical_digests.json holds SHA-256 digests of the ranked top-1000
 parents) that the SEQUENTIAL canonical specification in oracle/ produced for BASELINE configs[3] (40 clusters x 20
 samples) and configs[4] (120 x 64), seed 2026, at the reference's default cap and at 2^22 trees.  The GPU must
 reproduce every digest bit for bit -- with the lower bound on and off (LICHEE_NO_PRUNE), with and without the
-single-block scheduler (LICHEE_NO_NARROW), with and without the stored-bound prefilter (LICHEE_NO_PREFILTER), and with a frontier
-capacity of 2^16 items -- so a bound or scheduler bug
+single-block scheduler (LICHEE_NO_NARROW), with and without the stored-bound prefilter (LICHEE_NO_PREFILTER), with and
+without the second stream that checks the next chunk ahead (LICHEE_NO_PREFETCH), and with a frontier capacity of 2^16 items -- so a bound or scheduler bug
 that drops a winner cannot pass.  At 2^26 trees, where the CPU cannot follow, bound on / off must agree with each other."""
 import json
 import os
@@ -20,12 +20,13 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = json.load(open(os.path.join(HERE, "golden", "canonical_digests.json")))["cases"]
 ENVS = ({}, {"LICHEE_NO_PRUNE": "1"}, {"LICHEE_NO_NARROW": "1"}, {"LICHEE_NO_PRUNE": "1", "LICHEE_NO_NARROW": "1"},
-        {"LICHEE_NO_PREFILTER": "1"})
+        {"LICHEE_NO_PREFILTER": "1"}, {"LICHEE_NO_PREFETCH": "1"}, {"LICHEE_NO_PREFETCH": "1", "LICHEE_NO_PRUNE": "1"})
+SWITCHES = ("LICHEE_NO_NARROW", "LICHEE_NO_PRUNE", "LICHEE_NO_PREFILTER", "LICHEE_NO_PREFETCH")
 
 
 def canonical_run(net, prm, cap, monkeypatch, env=None, **kw):
     import lichee_b200
-    for k in ("LICHEE_NO_NARROW", "LICHEE_NO_PRUNE", "LICHEE_NO_PREFILTER"):
+    for k in SWITCHES:
         monkeypatch.delenv(k, raising=False)
     for k, v in (env or {}).items():
         monkeypatch.setenv(k, v)
@@ -36,7 +37,7 @@ def canonical_run(net, prm, cap, monkeypatch, env=None, **kw):
         return st, lichee_b200.top_list_sha256(s.trees())
     finally:
         s.close()
-        for k in ("LICHEE_NO_NARROW", "LICHEE_NO_PRUNE", "LICHEE_NO_PREFILTER"):
+        for k in SWITCHES:
             monkeypatch.delenv(k, raising=False)
 
 
@@ -58,8 +59,9 @@ def test_bound_on_and_off_agree_at_2_to_26_trees(built, monkeypatch, clusters, s
     net, prm = make_instance(clusters, samples, seed=2026)
     a, da = canonical_run(net, prm, 1 << 26, monkeypatch)
     b, db = canonical_run(net, prm, 1 << 26, monkeypatch, {"LICHEE_NO_PRUNE": "1"})
-    assert a.num_trees == b.num_trees == 1 << 26
-    assert da == db
+    c, dc = canonical_run(net, prm, 1 << 26, monkeypatch, {"LICHEE_NO_PREFETCH": "1"})
+    assert a.num_trees == b.num_trees == c.num_trees == 1 << 26
+    assert da == db == dc
 
 
 @pytest.mark.skipif(not os.environ.get("LICHEE_SLOW"), reason="3.5*10^7 grow() calls on one warp: minutes; set LICHEE_SLOW=1")
