@@ -520,7 +520,8 @@ def main():
             "device_ms_per_step": sum(s.kernel_ms_total for s in stats) / args.steps,
             "timing": "value/ms_per_step: host clock between (barrier + cuda synchronize) pairs around the K steps, max over ranks "
                       "(it contains everything, host round trips and the merge included); device_ms_per_step and kernel_ms_per_step: "
-                      "CUDA events on the library's own stream (rank 0)",
+                      "CUDA events on the library's own streams (rank 0); the check column includes the check2_kernel launches that "
+                      "run ahead on the second stream BESIDE the other columns, so the columns add up to more than the step",
         }
         if per_rank is not None:
             line["per_rank"] = per_rank
