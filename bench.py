@@ -472,7 +472,10 @@ def main():
         ms = [sum(s.kernel_ms[i] for s in stats) for i in range(5)]
         nl = [sum(s.kernel_launches[i] for s in stats) for i in range(5)]
         by = [sum(s.kernel_bytes[i] for s in stats) for i in range(5)]
-        dom = max(range(5), key=lambda i: ms[i])
+        # dominant kernel: leaf_kernel (largest share of the committed ncu launch list, profiles/r02_launches_summary.txt).  The
+        # check column cannot be used to pick it: its check2_kernel launches run ahead on a low-priority second stream, so
+        # their event times contain the waiting for SMs the main stream holds.
+        dom = K.index("leaf") if "leaf" in K else max(range(5), key=lambda i: ms[i])
         peak, peak_src = measured_peak()
         achieved = by[dom] / (ms[dom] * 1e-3) / 1e9 if ms[dom] > 0 else 0.0
         traffic = None
