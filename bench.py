@@ -119,7 +119,7 @@ def ncu_note():
                 return r[1:-1]
         return None
     parts = []
-    for label, f in (("leaf_kernel (a burst / the chunk after it / an ordinary chunk)", "r02_leaf_kernel_ncu_full.csv"),
+    for label, f in (("leaf_kernel (a burst / a second burst / a short ordinary chunk)", "r02_leaf_kernel_ncu_full.csv"),
                      ("check2_kernel", "r02_check2_kernel_ncu_full.csv"), ("replay_kernel (one warp)", "r02_replay_kernel_ncu_full.csv")):
         iss = pick(f, "smsp__issue_active.avg.pct_of_peak_sustained_active")
         wrp = pick(f, "sm__warps_active.avg.pct_of_peak_sustained_active")
