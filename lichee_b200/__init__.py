@@ -182,6 +182,46 @@ class PHYTree:
     __str__ = toString
 
 
+class RankedTrees:
+    """The ranked list as a read-only sequence over the arrays the ABI filled (scores, sequence numbers, parent and
+    insertion-order rows): a PHYTree object is made when an entry is first looked at, so handing back a list of a
+    thousand trees costs two array allocations and one library call, not a thousand constructor calls."""
+
+    __slots__ = ("_sc", "_seq", "_par", "_ord", "_made")
+
+    def __init__(self, sc, seq, par, order):
+        self._sc, self._seq, self._par, self._ord = sc, seq, par, order
+        self._made = {}
+
+    def __len__(self):
+        return len(self._sc)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[j] for j in range(*k.indices(len(self)))]
+        n = len(self)
+        if k < 0:
+            k += n
+        if not 0 <= k < n:
+            raise IndexError("ranked tree index out of range")
+        t = self._made.get(k)
+        if t is None:
+            t = self._made[k] = PHYTree(float(self._sc[k]), self._par, self._ord, int(self._seq[k]), k)
+        return t
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+    def __eq__(self, other):
+        try:
+            return len(self) == len(other) and all(a is b for a, b in zip(self, other))
+        except TypeError:
+            return NotImplemented
+
+    def __repr__(self):
+        return f"RankedTrees({len(self)} trees)"
+
+
 def top_list_sha256(trees, with_seq=True):
     """SHA-256 of a ranked list: scores (f64) | seq (i64) | parents (i32), ranked order.  bench.py prints it for
     every step and tests/golden/canonical_digests.json pins it for the benched shapes.  with_seq=False leaves the
@@ -189,6 +229,12 @@ def top_list_sha256(trees, with_seq=True):
     counts are compared on scores and trees."""
     import hashlib
     h = hashlib.sha256()
+    if isinstance(trees, RankedTrees):       # the same bytes, straight from the arrays
+        h.update(np.ascontiguousarray(trees._sc, dtype=np.float64).tobytes())
+        if with_seq:
+            h.update(np.ascontiguousarray(trees._seq, dtype=np.int64).tobytes())
+        h.update(np.ascontiguousarray(trees._par, dtype=np.int32).tobytes())
+        return h.hexdigest()
     h.update(np.array([t.errorScore for t in trees], dtype=np.float64).tobytes())
     if with_seq:
         h.update(np.array([t.seq for t in trees], dtype=np.int64).tobytes())
@@ -286,7 +332,7 @@ class LineageSearch:
         seq = np.zeros(m, dtype=np.int64)
         _ck(lib().lichee_search_get_trees(self._h, 0, m, sc.ctypes.data, par.ctypes.data, order.ctypes.data,
                                           seq.ctypes.data))
-        return [PHYTree(s_, par, order, q_, k) for k, (s_, q_) in enumerate(zip(sc.tolist(), seq.tolist()))]
+        return RankedTrees(sc, seq, par, order)
 
     def record_bytes(self):
         return int(lib().lichee_record_bytes(self._h))

@@ -362,11 +362,8 @@ check_kernel(DevNet net, int level, const unsigned *__restrict__ items, long lon
 // ------------------------------------------------------------------------------------------
 constexpr unsigned kCountMask = 0x3fffffffu;   // last-level counts carry a flag bit
 constexpr unsigned kBounded = 0x40000000u;     // no tree below this item can enter the ranked list
-// what a scan adds up: the plain count, or (last level) the trees of the items that are not bounded, i.e.
+// what a scan adds up: the plain count, or (last level, live mode) the trees of the items that are not bounded, i.e.
 // an upper bound on the candidates a chunk can append
-__device__ __forceinline__ unsigned scan_value(unsigned x, int live_only) {
-    return (live_only && (x & kBounded)) ? 0u : x & kCountMask;
-}
 // Live mode with the stored bounds (last level): an item whose base's bound exceeds what the CURRENT threshold
 // admits yields no candidate either -- the same test leaf_kernel applies before it touches the item -- so the chunk
 // extends over everything a burst earlier in the fill has made hopeless.
@@ -2826,6 +2823,7 @@ struct lichee_search {
     int n = 0, S = 0, SP = 32, L = 0, stride = 16, device = 0;
     lichee_search_params prm{};
     std::vector<int> sigma;                  // node at position t
+    std::vector<uint8_t> ibyte;              // item_byte(t, stride / 4) of every position (get_tree reads a thousand trees: no divisions there)
     std::vector<std::vector<int>> cands;     // candidate parents per position
     bool no_trees = false;                   // some node has no parent at all
     bool ran = false;
@@ -3843,6 +3841,8 @@ int lichee_search_create(lichee_search **out, int32_t n, int32_t S, const int32_
     h->L = n - 1;
     h->SP = S <= 32 ? 32 : 64;
     h->stride = std::max(16, ((h->L + 15) / 16) * 16);
+    h->ibyte.resize((size_t)std::max(1, h->L));
+    for (int t = 0; t < h->L; t++) h->ibyte[t] = (uint8_t)item_byte(t, h->stride >> 2);
     // a tree exists only if the root has children (PHYNetwork.java:557) and every other node a parent
     h->no_trees = radj[0].empty() && n > 1;
     h->cyclic = cyclic;
@@ -4145,11 +4145,10 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
     if (h->ref_result) {
         // A = treeNodes (without the root) in the order the nodes joined the tree, B = their parents, as rows
         const uint8_t *a = h->h_tree.data() + (size_t)k * 2 * h->stride, *bp = a + h->stride;
-        const int W = h->stride >> 2;
         if (parent) parent[0] = -1;
         if (order) order[0] = 0;
         for (int i = 0; i < h->L; i++) {
-            const int qa = a[item_byte(i, W)], qb = bp[item_byte(i, W)];
+            const int qa = a[h->ibyte[i]], qb = bp[h->ibyte[i]];
             if (qa < 1 || qa > h->L || qb > h->L) { set_err("corrupt tree record: rows %d <- %d at position %d", qa, qb, i); return LICHEE_ERR_STATE; }
             const int node = h->sigma[qa - 1];
             if (parent) parent[node] = qb == 0 ? 0 : h->sigma[qb - 1];
@@ -4161,7 +4160,7 @@ int lichee_search_get_tree(const lichee_search *h, int32_t k, double *score, int
     // byte item_byte(t) holds the row index q of the parent of sigma[t]; q = 0 root, q = j+1 node sigma[j]
     int par_of[kMaxN];
     for (int t = 0; t < h->L; t++) {
-        const int q = b[item_byte(t, h->stride >> 2)];
+        const int q = b[h->ibyte[t]];
         if (q > h->L) { set_err("corrupt tree record: parent row %d at position %d", q, t); return LICHEE_ERR_STATE; }
         par_of[t] = q == 0 ? 0 : h->sigma[q - 1];
     }
