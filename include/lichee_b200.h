@@ -107,7 +107,9 @@ typedef struct lichee_search_stats {
     double  kernel_ms_total;     /* CUDA-event time of the whole device search                  */
     /* per kernel class (LICHEE_K_*): summed CUDA-event time on the launching stream, launches,
      * and ALGORITHMIC bytes (frontier items + masks each launch must read and write once)       */
-    double  kernel_ms[LICHEE_NUM_KERNELS];
+    double  kernel_ms[LICHEE_NUM_KERNELS];   /* CUDA events per kernel class; the check class includes launches that run ahead on the
+                                               library's second stream, BESIDE the other classes: the classes can add up to more
+                                               than kernel_ms_total                                                              */
     int64_t kernel_launches[LICHEE_NUM_KERNELS];
     int64_t kernel_bytes[LICHEE_NUM_KERNELS];
     uint32_t status;
