@@ -3628,11 +3628,16 @@ int run_reference_order(lichee_search *h, bool &completed) {
             rec_cap = kReplayRecCap;
         }
     }
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    st.kernel_ms_total = ms;
+    if (fused) {
+        // one launch, already synchronized: its own time is the device time (no second event, no second round trip)
+        st.kernel_ms_total = st.kernel_ms[LICHEE_K_CHECK];
+    } else {
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        st.kernel_ms_total = ms;
+    }
     st.num_trees = num_trees;
     st.num_grow_calls = num_grow;
     st.num_checks = num_checks;
