@@ -2347,14 +2347,27 @@ replay_kernel(const __grid_constant__ ReplayArgs a) {
     // the state is worked on in shared memory when it fits, else in place in the device copy
     unsigned char *blob = BS ? smem_raw + vaf_bytes : a.blob_dst;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.vaf);
-        uint4 *dst = reinterpret_cast<uint4 *>(vaf_s);
-        for (unsigned i = threadIdx.x; i < vaf_bytes / 16; i += blockDim.x) dst[i] = src[i];
-        if (BS || a.blob_src != a.blob_dst) {
-            const uint4 *bs = reinterpret_cast<const uint4 *>(a.blob_src);
-            uint4 *bd = reinterpret_cast<uint4 *>(blob);
-            for (unsigned i = threadIdx.x; i < lay.total / 16; i += blockDim.x) bd[i] = bs[i];
-        }
+        // The first launch reads the matrix and the initial state straight from pinned host memory: eight loads per
+        // thread are requested before the first one is stored, so a small search pays one or two bus round trips here,
+        // not one per 2 KB.
+        auto stage = [&](const uint4 *src, uint4 *dst, unsigned n16) {
+            for (unsigned base = 0; base < n16; base += blockDim.x * 8) {
+                uint4 r[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned i = base + j * blockDim.x + threadIdx.x;
+                    if (i < n16) r[j] = src[i];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned i = base + j * blockDim.x + threadIdx.x;
+                    if (i < n16) dst[i] = r[j];
+                }
+            }
+        };
+        stage(reinterpret_cast<const uint4 *>(a.vaf), reinterpret_cast<uint4 *>(vaf_s), vaf_bytes / 16);
+        if (BS || a.blob_src != a.blob_dst)
+            stage(reinterpret_cast<const uint4 *>(a.blob_src), reinterpret_cast<uint4 *>(blob), lay.total / 16);
         if (a.first && threadIdx.x == 0) {
             TopMeta *meta = a.meta;
             meta->count = 0; meta->pad = 0; meta->tau = INFINITY; meta->n_cand = 0; meta->n_valid = 0;
