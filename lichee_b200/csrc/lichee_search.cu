@@ -1287,13 +1287,13 @@ emit2_kernel(DevNet net, const unsigned *__restrict__ items, long long n_items, 
 }
 
 // Last level: the pass mask + count of every item were written by emit2_kernel (for the scan that numbers
-// the valid trees); this kernel scores the trees of the items that are not bounded and appends those that
-// beat the threshold with a provisional sequence number; seq_fixup_kernel turns that into the canonical
-// one once the scan has run.
+// the valid trees); this kernel totals the trees of the items that are not bounded and appends those that
+// beat the threshold as 16-byte candidates; seq_fixup_kernel takes the square roots and gives them their canonical
+// sequence numbers once the scan has run.
 template <int SPL>
 __global__ void __launch_bounds__(kThreads, 2)
 leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__restrict__ fit, long long item_base,
-            const unsigned *__restrict__ lcnt, const double *__restrict__ lbound, int part, TopMeta *meta,
+            const unsigned *__restrict__ lcnt, const double *__restrict__ lbound, TopMeta *meta,
             int num_save, uint4 *__restrict__ cands, long long cand_cap, int run_len_arg, const unsigned *__restrict__ ref_item) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *vaf_s = reinterpret_cast<double *>(smem_raw);
@@ -3402,7 +3402,7 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
             int run_len = 32;    // (measured: runs of 256 items left a tail of ~1 ms per step; a run of bounded items costs a few instructions)
             if (h->no_prefilter) run_len = -run_len;
             leaf_kernel<SPL><<<grid, kThreads, h->smem_leaf, h->stream>>>(
-                h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], R, h->d_meta(), h->prm.num_save,
+                h->net, items, h->d_scan(), h->head[lv], lcnt, static_cast<const double *>(h->b_lbound.p) + h->head[lv], h->d_meta(), h->prm.num_save,
                 static_cast<uint4 *>(h->b_c16.p), cand_cap, run_len, fill_ref);
             CK(cudaGetLastError());
             st.kernel_launches[LICHEE_K_LEAF]++;
