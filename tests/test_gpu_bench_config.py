@@ -85,3 +85,21 @@ def test_config3_identical_to_the_reference_with_a_large_budget(built):
     h.update(np.array([t.treeNodes for t in trees], dtype=np.int32).tobytes())
     h.update(np.array([t.seq for t in trees], dtype=np.int64).tobytes())
     assert h.hexdigest() == ref["top100_sha256"]
+
+
+@pytest.mark.skipif(not os.environ.get("LICHEE_SLOW"), reason="10^8 grow() calls on one warp: minutes; set LICHEE_SLOW=1")
+def test_config4_identical_to_the_reference_with_the_full_budget(built):
+    """BASELINE configs[4] (120 x 64, -c) with the reference's own caps and a replay budget that covers them: the
+    reference spends its whole MAX_NUM_GROW_CALLS = 10^8 without finding a single valid tree
+    (tests/golden/reference_caps.json, literal port, 976 s of one core) -- and so does the library when it is told to
+    follow the reference to the end: no tree, the grow-call cap reported, the canonical fallback not taken."""
+    import lichee_b200
+    ref = json.load(open(os.path.join(HERE, "golden", "reference_caps.json")))["results"]["120x64"]
+    net, prm = make_instance(120, 64, seed=2026)
+    s = lichee_b200.LineageSearch(net.adj, np.array(net.aaf), prm.vaf_error_margin, num_save=1000, ref_order_budget=(1 << 27))
+    st = s.run()
+    trees = s.trees()
+    s.close()
+    assert not (st.status & 4) and st.status & 2
+    assert (st.num_trees, len(trees)) == (ref["n_trees"], 0) and ref["n_trees"] == 0
+    assert st.num_grow_calls == ref["n_grow"] == 100000000
