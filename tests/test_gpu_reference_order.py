@@ -109,6 +109,25 @@ def test_random_digraphs_caps_and_cycles(built):
             assert a["num_trees"] == b["num_trees"] and a["num_grow_calls"] == b["num_grow_calls"]
 
 
+def test_random_digraphs_33_to_64_nodes(built):
+    """Sparse digraphs with 33..64 nodes (more than one 32-node group per list scan of the replay, node lists that do not
+    fill the last group), a quarter of them cyclic, searched to the end or into a grow-call cap: identical to the literal
+    port."""
+    rng = random.Random(64)
+    done = 0
+    for it in range(40):
+        n = rng.randint(33, 64)
+        S = rng.choice([1, 4, 20, 33, 64])
+        adj, vaf = rand_graph(rng, n, S, rng.choice([0.04, 0.06, 0.09]), rng.choice([0.02, 0.05]), rng.random() < 0.25)
+        for v in range(1, n):                                   # every node reachable: an edge from the root if it has none
+            if not any(v in a for a in adj):
+                adj[0].append(v)
+        st, trees, ref = assert_identical_to_reference(adj, vaf, rng.choice([0.05, 0.1]), num_save=rng.choice([1, 100]),
+                                                       max_trees=rng.choice([1000, 100000]), max_grow=200000, ref_order_budget=1 << 20)
+        done += 0 if ref["stopped"] else 1
+    assert done >= 5
+
+
 def test_many_trees_several_batches_and_ties(built):
     """More trees than one record batch holds (the replay pauses, the batch is scored and merged, the replay
     resumes), -s 1000, zero-margin ties: RK26 -c (28080 trees, 99 of the top 100 scores tie) and synthetic
