@@ -1634,6 +1634,13 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
     if (lane == 0 && my_eval) atomicAdd(&meta->n_eval, my_eval);
 }
 
+// A survivor's record from its 16-byte candidate and its keys (score bits, sequence number).
+__device__ __forceinline__ Cand cand_record(const uint4 &r, unsigned long long k0, unsigned long long k1, int part) {
+    Cand c;
+    c.score = __longlong_as_double((long long)k0); c.seq = (long long)k1; c.part = part; c.origin = r.z; c.pstar = r.w & 0xffu; c.pad = 0;
+    return c;
+}
+
 // Turns the 16-byte candidates of leaf_kernel into ranked-list records: score = sqrt_rn(total), the canonical sequence
 // number (rank among the valid trees) now that the scan has numbered the items; retires the ones beyond
 // Parameters.MAX_NUM_TREES.  Also writes the selection keys (score bits, seq; ~0 for an empty slot) as two plain
@@ -1642,7 +1649,8 @@ leaf_kernel(DevNet net, const unsigned *__restrict__ items, const ScanOut *__res
 __global__ void __launch_bounds__(256)
 seq_fixup_kernel(const uint4 *__restrict__ c16, Cand *__restrict__ cands, long long m, long long item_base,
                  const uint4 *__restrict__ mask, const unsigned *__restrict__ off, long long seq_base, long long max_trees,
-                 unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1, TopMeta *meta, int num_save, int part) {
+                 unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1, TopMeta *meta, int num_save, int part,
+                 int write_records) {
     __shared__ unsigned long long mn_s[8], mx_s[8];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long kb = ~0ull, seqk = ~0ull;
@@ -1672,7 +1680,7 @@ seq_fixup_kernel(const uint4 *__restrict__ c16, Cand *__restrict__ cands, long l
             }
         }
         key0[t] = kb; key1[t] = seqk;
-        cands[t] = c;
+        if (write_records) cands[t] = c;       // (a long list: only the survivors' records are built, by radix12_compact)
     }
     // key range of the launch: one pair of atomics per block
     unsigned long long mn = live ? kb : ~0ull, mx = live ? kb : 0ull;
@@ -2148,7 +2156,7 @@ radix12_pass(const unsigned long long *__restrict__ key0, const unsigned long lo
 }
 
 __global__ void __launch_bounds__(256)
-radix12_compact(const Cand *__restrict__ cands, const unsigned long long *__restrict__ key0,
+radix12_compact(const uint4 *__restrict__ c16, int part, const unsigned long long *__restrict__ key0,
                 const unsigned long long *__restrict__ key1, long long m, Radix12State *st, Cand *__restrict__ out, long long out_cap) {
     if (!st->done) return;
     const unsigned long long t0 = st->thresh[0], t1 = st->thresh[1];
@@ -2165,8 +2173,9 @@ radix12_compact(const Cand *__restrict__ cands, const unsigned long long *__rest
             const unsigned long long k0 = k0v[j];
             if (k0 == ~0ull) continue;
             if (k0 < t0 || (k0 == t0 && key1[i] <= t1)) {
+                const unsigned long long k1 = key1[i];
                 const unsigned long long slot = atomicAdd(&st->kept, 1ull);
-                if ((long long)slot < out_cap) out[slot] = cands[i];   // only the survivors' records are read
+                if ((long long)slot < out_cap) out[slot] = cand_record(c16[i], k0, k1, part);   // only the survivors' records are built
             }
         }
     }
@@ -3032,7 +3041,10 @@ int run_radix_select(lichee_search *h, long long &m, bool &used) {
 
 // The 12-bit form for last-level chunks (leaf_kernel recorded the key range in the meta block).  Falls back to
 // run_radix_select when equal scores overflow the tile.
-int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq_lo, long long seq_hi) {
+// (the candidates' 32-byte records do not exist yet: radix12_compact builds the survivors'; `materialize` writes them
+//  all, for the byte-wise fallback)
+template <class F>
+int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq_lo, long long seq_hi, int part, F materialize) {
     used = false;
     if (ensure(h, h->b_radix12, sizeof(Radix12State)) != LICHEE_OK ||
         ensure(h, h->b_cands[1], sizeof(Cand) * (size_t)kSelTile) != LICHEE_OK)
@@ -3047,7 +3059,7 @@ int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq
     for (int round = 0; round < 2; round++) {           // 6 + 6 digits cover the 128 key bits; finished passes return at once
         const unsigned long long *k0 = static_cast<const unsigned long long *>(h->b_key0.p), *k1 = static_cast<const unsigned long long *>(h->b_key1.p);
         for (int p = 0; p < 6; p++) radix12_pass<<<grid, 256, 0, h->stream>>>(k0, k1, m, st, (unsigned)kSelTile);
-        radix12_compact<<<grid, 256, 0, h->stream>>>(h->d_cands(0), k0, k1, m, st, h->d_cands(1), (long long)kSelTile);
+        radix12_compact<<<grid, 256, 0, h->stream>>>(static_cast<const uint4 *>(h->b_c16.p), part, k0, k1, m, st, h->d_cands(1), (long long)kSelTile);
         CK(cudaGetLastError());
         h->stats.num_launches += 7;
         h->stats.kernel_launches[LICHEE_K_SELECT] += 7;
@@ -3063,7 +3075,10 @@ int run_radix12_select(lichee_search *h, long long &m, bool &used, long long seq
         fprintf(stderr, "radix12: m=%lld done=%u word=%d shift=%d kept=%llu below=%llu k=%llu thresh=%016llx/%llu\n", m, hs.done, hs.word,
                 hs.shift, hs.kept, hs.below, hs.k, hs.thresh[0], hs.thresh[1]);
     }
-    if (!rd.done || rd.kept > (unsigned long long)kSelTile) return run_radix_select(h, m, used);
+    if (!rd.done || rd.kept > (unsigned long long)kSelTile) {
+        if (materialize() != LICHEE_OK) return LICHEE_ERR_CUDA;
+        return run_radix_select(h, m, used);
+    }
     m = (long long)rd.kept;
     used = true;
     return LICHEE_OK;
@@ -3447,16 +3462,23 @@ int run_search(lichee_search *h, int R, int P, bool keep) {
                 if (ensure(h, h->b_key0, 8 * (size_t)m) != LICHEE_OK || ensure(h, h->b_key1, 8 * (size_t)m) != LICHEE_OK ||
                     ensure(h, h->b_cands[0], sizeof(Cand) * (size_t)m) != LICHEE_OK)
                     return LICHEE_ERR_CUDA;
-                seq_fixup_kernel<<<(int)((m + 255) / 256), 256, 0, h->stream>>>(static_cast<const uint4 *>(h->b_c16.p), h->d_cands(0), m, h->head[lv], lmask,
-                                                                             h->d_off(), seq_base, h->prm.max_num_trees,
-                                                                             static_cast<unsigned long long *>(h->b_key0.p),
-                                                                             static_cast<unsigned long long *>(h->b_key1.p), h->d_meta(),
-                                                                             h->prm.num_save, R);
-                CK(cudaGetLastError());
-                st.num_launches++;
+                // a long list gets keys only; the 32-byte records are built for the survivors of the radix selection
+                const long long m_all = m;
+                const long long item0 = h->head[lv];
+                auto fixup = [&](int write_records) -> int {
+                    seq_fixup_kernel<<<(int)((m_all + 255) / 256), 256, 0, h->stream>>>(static_cast<const uint4 *>(h->b_c16.p), h->d_cands(0), m_all, item0, lmask,
+                                                                                 h->d_off(), seq_base, h->prm.max_num_trees,
+                                                                                 static_cast<unsigned long long *>(h->b_key0.p),
+                                                                                 static_cast<unsigned long long *>(h->b_key1.p), h->d_meta(),
+                                                                                 h->prm.num_save, R, write_records);
+                    CK(cudaGetLastError());
+                    st.num_launches++;
+                    return LICHEE_OK;
+                };
+                if (fixup(m <= kSelTile ? 1 : 0) != LICHEE_OK) return LICHEE_ERR_CUDA;
                 int src = 0;
                 bool radix = false;
-                if (m > kSelTile && run_radix12_select(h, m, radix, seq_base, seq_base + std::max<long long>(leaf_total, 1) - 1) != LICHEE_OK)
+                if (m > kSelTile && run_radix12_select(h, m, radix, seq_base, seq_base + std::max<long long>(leaf_total, 1) - 1, R, [&]() { return fixup(1); }) != LICHEE_OK)
                     return LICHEE_ERR_CUDA;
                 if (radix) src = 1;
                 else if (run_tournament(h, m, src) != LICHEE_OK) return LICHEE_ERR_CUDA;
