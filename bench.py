@@ -8,10 +8,10 @@ One "step" = one whole tree search of that network: enumerate spanning trees in 
 sum-rule check every candidate extension, score every complete valid tree, keep the top 1000.
 Parameters.MAX_NUM_TREES is raised from the reference's 100000 to --max-trees so that a step is
 long enough to measure a B200 (with the reference's default a step is ~1 ms of launch latency).
-The step runs in CANONICAL order (ref_order_budget = -1): the library's default reference-order replay
-cannot finish on this network -- the literal port of the reference needs its full 10^8 grow() calls and
-finds no tree (tests/golden/reference_caps.json) -- so the default mode would fall back to exactly this
-search after spending its replay budget.  The reference-order mode is measured on the networks where the
+The step runs in CANONICAL order (ref_order_budget = -1): on this network the reference's own search spends its
+full 10^8 grow() calls and finds no tree (literal port, tests/golden/reference_caps.json; the library's
+reference-order replay reproduces that when it is given the budget, tests/test_gpu_bench_config.py, opt-in) -- the
+default mode gives up after its replay budget and falls back to exactly this search.  The reference-order mode is measured on the networks where the
 reference itself finishes: `bundled_datasets_build_search_ms` (identical output, checked in the run).
 
   top_list_sha256     : digest of the ranked top-s list; every timed step must produce the same one, and the
@@ -497,8 +497,10 @@ def main():
                        "parallelism": f"frontier slices x{world}" if world > 1 else "single GPU",
                        "l2": "frontier chunks are produced and consumed once per step; every level buffer is rewritten "
                              "between timed steps (working set of a step > 126 MB L2)",
-                       "order": "canonical (ref_order_budget=-1): the reference-order replay cannot finish on this network "
-                                "(literal port: 10^8 grow() calls, 0 valid trees, 976 s; tests/golden/reference_caps.json)",
+                       "order": "canonical (ref_order_budget=-1): followed to its own end the reference's search spends its whole "
+                                "MAX_NUM_GROW_CALLS = 10^8 on this network and finds no valid tree (literal port 976 s, "
+                                "tests/golden/reference_caps.json; the library's reference-order replay 328 s with the same "
+                                "result, profiles/r02_config4_reference_order.log)",
                        "valid_trees_per_step": st0.num_trees * world if world > 1 else st0.num_trees,
                        "complete_trees_scored_per_s": scored_all / t_dev},
             "top_list_sha256": top_digest,
